@@ -1,0 +1,179 @@
+/*
+ * uttt_b200.h -- C ABI of libuttt_b200.so, the B200 (sm_100a) self-play engine for
+ * Ultimate Tic-Tac-Toe.  This is the drop-in boundary: every entry point replaces a
+ * piece of the reference's pybind11 module `uttt_cpp` (cpp/python_bindings.cpp:49-107)
+ * or of the Python glue that drives it (pv_mcts_cpp.py, self_play_cpp.py).
+ * Citations are <file>:<line> in the reference repository.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; uttt_last_error()
+ *     returns a message for the calling thread's last failure.
+ *   - "packed state" = 8 x uint32 (32 B), see csrc/uttt_rules.cuh:
+ *       w0..w2 mover stones, w3..w5 opponent stones (3 sub-boards/word, 9 bits each),
+ *       w6 = main_board_pieces | main_board_enemy_pieces<<9 | (active_board+1)<<18, w7 = 0.
+ *   - "legal mask" = 4 x uint32 per state: words 0..2 hold 27 action bits each
+ *     (action id = 27*word + bit = 9*board + cell), word 3 = number of legal moves.
+ *   - *_dev pointers are CUDA device pointers owned by the caller (e.g. torch tensors);
+ *     `stream` is a cudaStream_t (NULL = default stream); device calls are asynchronous
+ *     on that stream unless stated otherwise.
+ *   - there is no CPU fallback: device entry points fail if no sm_100 GPU is present.
+ */
+#ifndef UTTT_B200_H
+#define UTTT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UTTT_ABI_VERSION 1
+
+/* evaluators for search / self-play */
+#define UTTT_EVAL_NET_BF16 0 /* DualNetwork forward, tcgen05 bf16 implicit-GEMM trunk          */
+#define UTTT_EVAL_NET_FP32 1 /* DualNetwork forward, fp32 CUDA-core trunk ("parity" numerics)  */
+#define UTTT_EVAL_HASH     2 /* deterministic integer-hash evaluator (search parity oracle mode) */
+#define UTTT_EVAL_HOST     3 /* caller evaluates leaves (uttt_mcts_get_leaves/put_results)     */
+
+/* self-play flags */
+#define UTTT_SP_CORRECT_TERMINAL_SIGN 1 /* opt out of the reference's inverted terminal sign (cpp/uttt_mcts.cpp:19-21) */
+
+typedef struct uttt_engine uttt_engine;
+
+const char *uttt_last_error(void);
+int uttt_abi_version(void);
+/* 0 iff `device` exists and is compute capability 10.x */
+int uttt_device_check(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Single-state helpers (host arithmetic on ONE packed state; back the `uttt_cpp.State`
+ * object of the Python shim -- cpp/python_bindings.cpp:54-74).  Not a device fallback:
+ * every batch / search / self-play entry point below runs on the GPU only.
+ * ---------------------------------------------------------------------------------------- */
+int uttt_state_init(uint32_t *state);                                             /* cpp/uttt_game.cpp:9-19   */
+int uttt_state_next(const uint32_t *state, int action, uint32_t *out);            /* cpp/uttt_game.cpp:97-145 */
+int uttt_state_legal_actions(const uint32_t *state, int32_t *out81, int *n_out);  /* cpp/uttt_game.cpp:148-191 */
+/* bit0 is_lose, bit1 is_draw, bit2 is_done, bit3 is_first_player (cpp/uttt_game.cpp:77-94) */
+int uttt_state_flags(const uint32_t *state, int *flags_out);
+int uttt_state_encode(const uint32_t *state, float *out243);                      /* cpp/uttt_game.cpp:244-280 */
+int uttt_state_to_string(const uint32_t *state, char *buf, int cap, int *len_out);/* cpp/uttt_game.cpp:194-241 */
+
+/* ------------------------------------------------------------------------------------------
+ * Rules kernels over arrays of packed states in HBM (replace UTTT::State, cpp/uttt_game.cpp)
+ * ---------------------------------------------------------------------------------------- */
+/* out[i] = next(states[i], actions[i])                      cpp/uttt_game.cpp:97-145 */
+int uttt_game_step(const uint32_t *states_dev, const int32_t *actions_dev, uint32_t *out_dev,
+                   int64_t n, void *stream);
+/* masks[i] = legal mask (4 words), status[i] = 0 ongoing / 1 lose / 2 draw
+ *                                                            cpp/uttt_game.cpp:77-89,148-191 */
+int uttt_game_legal_mask(const uint32_t *states_dev, uint32_t *masks_dev, uint8_t *status_dev,
+                         int64_t n, void *stream);
+/* planes[i] = float[9*9*3] HWC exactly as State::to_input_tensor   cpp/uttt_game.cpp:244-280 */
+int uttt_game_encode(const uint32_t *states_dev, float *planes_dev, int64_t n, void *stream);
+/* leaf gather: planes[i] = bf16[3*9*9] CHW, the network's input batch
+ *                                     (pv_mcts_cpp.py:47-60: reshape + stack + NHWC->NCHW) */
+int uttt_game_gather_planes(const uint32_t *states_dev, void *planes_bf16_dev, int64_t n, void *stream);
+/* n random playouts from the initial position, game ids game0..game0+n-1; action at ply t =
+ * legal[ philox4x32(key=(seed,0), ctr=(game_lo,game_hi,t,0)).x % n_legal ]; outputs per game:
+ * FNV-1a(64) digest over (action, legal mask, main flags/active) per ply + final state,
+ * ply count, result (0 draw / 1 first player won / 2 second player won). */
+int uttt_game_playout(uint32_t seed, uint64_t game0, int64_t n, uint64_t *digests_dev,
+                      int32_t *plies_dev, int32_t *results_dev, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Engine: trees, network weights, self-play slots -- all resident in HBM
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t device;        /* CUDA device ordinal */
+    int32_t n_slots;       /* concurrent trees / games */
+    int32_t max_sims;      /* largest evaluate_count that will be requested */
+    int32_t max_batch;     /* largest batch_size that will be requested */
+    int64_t max_games;     /* capacity of the self-play history buffers (games per run) */
+} uttt_config;
+
+int uttt_create(const uttt_config *cfg, uttt_engine **out);
+int uttt_destroy(uttt_engine *e);
+
+/* DualNetwork parameters (dual_network.py:47-75), fp32, PyTorch layouts, eval-mode BatchNorm.
+ * All pointers are device pointers if on_device != 0, else host pointers.
+ * bn arrays are [4][C]: weight, bias, running_mean, running_var (eps = 1e-5).            */
+typedef struct {
+    const float *conv_input_w;   /* (128,3,3,3)      */
+    const float *bn_input;       /* [4][128]         */
+    const float *res_conv_w;     /* (16,2,128,128,3,3): block, conv1/conv2, out, in, ky, kx */
+    const float *res_bn;         /* (16,2,4,128)     */
+    const float *policy_conv_w;  /* (2,128)          */
+    const float *policy_bn;      /* [4][2]           */
+    const float *policy_fc_w;    /* (81,162)         */
+    const float *policy_fc_b;    /* (81)             */
+    const float *value_conv_w;   /* (1,128)          */
+    const float *value_bn;       /* [4][1]           */
+    const float *value_fc1_w;    /* (256,81)         */
+    const float *value_fc1_b;    /* (256)            */
+    const float *value_fc2_w;    /* (1,256)          */
+    const float *value_fc2_b;    /* (1)              */
+} uttt_weights;
+
+/* folds BatchNorm, repacks to the tensor-core layouts; synchronous */
+int uttt_upload_weights(uttt_engine *e, const uttt_weights *w, int on_device);
+
+/* DualNetwork.forward on n packed states (dual_network.py:89-121 behind pv_mcts_cpp.py:37-78):
+ * policy[n][81] (softmax over all 81 actions), value[n].  mode = UTTT_EVAL_NET_BF16 / _FP32. */
+int uttt_net_forward(uttt_engine *e, const uint32_t *states_dev, int64_t n, int mode,
+                     float *policy_dev, float *value_dev, void *stream);
+
+/* ---- search: UTTT::pv_mcts_scores (cpp/uttt_mcts.cpp:84-196) over n_roots independent trees ----
+ * Synchronous.  roots/scores/counts/n_scores are HOST pointers.
+ * scores[i][0..n_scores[i]) follow legal_actions(root i) order; counts are the raw visit counts. */
+int uttt_mcts_search(uttt_engine *e, const uint32_t *roots, int32_t n_roots, int32_t evaluate_count,
+                     int32_t batch_size, float temperature, int32_t evaluator, float *scores /* n*81 */,
+                     int32_t *counts /* n*81 */, int32_t *n_scores /* n */);
+
+/* step-wise form for a caller-side evaluator (python_bindings.cpp:11-47 `wrap_python_inference`) */
+int uttt_mcts_begin(uttt_engine *e, const uint32_t *roots, int32_t n_roots, int32_t evaluate_count,
+                    int32_t batch_size);
+/* applies the results put since the last call, then descends every unfinished tree to its next
+ * unevaluated leaf; *n_pending = number of leaves now waiting (0 => search finished) */
+int uttt_mcts_advance(uttt_engine *e, int32_t *n_pending);
+/* pending leaves: packed states, k = number of queued copies of that leaf (cpp/uttt_mcts.cpp:121-127), tree id */
+int uttt_mcts_get_leaves(uttt_engine *e, uint32_t *states /* n_pending*8 */, int32_t *k /* n_pending */,
+                         int32_t *tree /* n_pending */);
+/* results for pending leaf i: per_copy==0 -> policy[i][81], value[i];
+ * per_copy!=0 -> policy[i][max_batch][81], value[i][max_batch] (row c feeds queued copy c) */
+int uttt_mcts_put_results(uttt_engine *e, const float *policy, const float *value, int per_copy);
+int uttt_mcts_finish(uttt_engine *e, float temperature, float *scores, int32_t *counts, int32_t *n_scores);
+
+/* cpp/uttt_mcts.cpp:199-216 on the device (fp32; bit-identical to the reference for T == 1) */
+int uttt_boltzman(const float *xs, int32_t n, float temperature, float *out);
+
+/* ---- self-play: self_play_cpp.py:34-130 for n_games games, all concurrent on the device ----
+ * Game ids game0..game0+n_games-1.  Per ply of game g (row g*81 + ply):
+ *   hist_states  packed state the move was chosen in                (self_play_cpp.py:56-59: x)
+ *   hist_counts  root visit counts by action id, uint16[81]          (self_play_cpp.py:63-83: pi = counts/sum)
+ *   hist_actions sampled action: pick = floor(philox(key=(seed,1),ctr=(g_lo,g_hi,ply,0)).x * sum / 2^32)
+ *                over the counts in legal order                      (self_play_cpp.py:86)
+ * hist_len[g] = plies, hist_final[g] = 1 if the final position is_lose (z0 = -1) else 0
+ *                                                                    (self_play_cpp.py:95-99)
+ * All hist_* pointers are HOST pointers (pinned memory recommended).  Synchronous.
+ * stats (may be NULL): [0] plies, [1] simulations, [2] evaluated leaves, [3] tree rounds */
+int uttt_selfplay_run(uttt_engine *e, int64_t n_games, uint64_t game0, int32_t evaluate_count,
+                      int32_t batch_size, uint32_t seed, int32_t evaluator, int32_t flags,
+                      uint32_t *hist_states, uint16_t *hist_counts, uint8_t *hist_actions,
+                      int32_t *hist_len, int8_t *hist_final, int64_t *stats);
+
+/* device-resident variant for benchmarking / multi-GPU pipelines: runs the same loop but leaves
+ * the history in the engine's HBM buffers; uttt_selfplay_fetch copies it out afterwards. */
+int uttt_selfplay_run_device(uttt_engine *e, int64_t n_games, uint64_t game0, int32_t evaluate_count,
+                             int32_t batch_size, uint32_t seed, int32_t evaluator, int32_t flags,
+                             int64_t *stats, void *stream);
+int uttt_selfplay_fetch(uttt_engine *e, int64_t n_games, uint32_t *hist_states, uint16_t *hist_counts,
+                        uint8_t *hist_actions, int32_t *hist_len, int8_t *hist_final);
+
+/* timing of the engine's own kernels during the last uttt_selfplay_run*: CUDA-event ms on the
+ * launching stream and launch counts; kind: 0 tree kernels, 1 trunk, 2 heads, 3 everything */
+int uttt_last_run_profile(uttt_engine *e, int kind, double *ms_out, int64_t *launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

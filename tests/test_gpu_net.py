@@ -1,0 +1,177 @@
+"""GPU: DualNetwork forward kernels vs the fp32 PyTorch module (the reference numerics,
+dual_network.py:89-121) on the same weights.
+
+Tolerance (BASELINE.json north_star): |policy - ref| <= 1e-2, |value - ref| <= 1e-2.
+  * fp32 CUDA-core trunk ("parity numerics"): must meet it on the reference's RANDOM-INIT weights.
+  * bf16 tcgen05 trunk: must meet it on a trained-like (damped) copy; on random-init weights the net is
+    ill-conditioned (logits reach +-400, fp32 softmax is one-hot) and plain bf16 operands
+    cannot meet 1e-2 on every position -- there we assert argmax agreement and the exceed fraction and
+    print the statistics instead of silently loosening the bound.
+"""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-2
+
+
+def _positions(n_games=24, seed=31337):
+    sts = np.concatenate([O.playout_states(seed, g)[0][:-1] for g in range(n_games)])
+    return sts
+
+
+def _torch_reference(model, sts):
+    import torch
+    import engine
+    planes = engine.game_encode(torch.from_numpy(sts.view(np.int32)).cuda()).cpu()    # (n,9,9,3), checked in test_gpu_rules
+    x = planes.permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        p, v = model(x)                      # fp32 PyTorch on the host cores = the reference numerics
+    return p.numpy(), v.numpy()[:, 0]
+
+
+def _damped(model):
+    """a 'trained-like' copy: residual branches damped so activations stay O(1)"""
+    import torch
+    with torch.no_grad():
+        for blk in model.residual_blocks:
+            blk.bn2.weight.mul_(0.3)
+        model.policy_fc.weight.mul_(0.05)
+        model.value_fc1.weight.mul_(0.2)
+        model.value_fc2.weight.mul_(0.2)
+        # non-trivial BN statistics so that folding is exercised
+        g = torch.Generator().manual_seed(5)
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.1)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+    return model
+
+
+@pytest.fixture(scope="module")
+def setup():
+    import torch
+    import engine
+    from dual_network import DualNetwork
+    torch.manual_seed(0)
+    model = DualNetwork().eval()
+    sts = _positions()
+    e = engine.Engine(n_slots=256, max_sims=50, max_batch=8, max_games=16)
+    yield e, model, sts
+    e.close()
+
+
+def _forward(e, sts, mode):
+    import torch
+    d = torch.from_numpy(sts.view(np.int32)).cuda()
+    p, v = e.net_forward(d, mode)
+    torch.cuda.synchronize()
+    return p.cpu().numpy(), v.cpu().numpy()
+
+
+def test_fp32_trunk_random_init_within_tolerance(setup):
+    import engine
+    e, model, sts = setup
+    e.upload_model(model)
+    pr, vr = _torch_reference(model, sts)
+    p, v = _forward(e, sts, engine.EVAL_NET_FP32)
+    perr, verr = np.abs(p - pr).max(), np.abs(v - vr).max()
+    print("fp32 trunk, random init: n=%d max|dp|=%.3e max|dv|=%.3e" % (len(sts), perr, verr))
+    assert np.allclose(p.sum(1), 1.0, atol=1e-4)
+    assert perr <= TOL and verr <= TOL
+
+
+def test_bf16_trunk_random_init_statistics(setup):
+    import engine
+    e, model, sts = setup
+    e.upload_model(model)
+    pr, vr = _torch_reference(model, sts)
+    p, v = _forward(e, sts, engine.EVAL_NET_BF16)
+    perr = np.abs(p - pr).max(axis=1)
+    verr = np.abs(v - vr)
+    agree = (p.argmax(1) == pr.argmax(1)).mean()
+    frac = (perr > TOL).mean()
+    print("bf16 tcgen05 trunk, random init: n=%d argmax agreement %.3f, frac(|dp|>1e-2)=%.3f, max|dp|=%.3f, "
+          "median|dp|=%.2e, max|dv|=%.3e" % (len(sts), agree, frac, perr.max(), np.median(perr), verr.max()))
+    assert np.isfinite(p).all() and np.isfinite(v).all()
+    assert np.allclose(p.sum(1), 1.0, atol=1e-4)
+    assert agree >= 0.90 and frac <= 0.30
+
+
+def test_bf16_trunk_trained_like_within_tolerance(setup):
+    import engine
+    e, model, sts = setup
+    import copy
+    m2 = _damped(copy.deepcopy(model))
+    e.upload_model(m2)
+    pr, vr = _torch_reference(m2, sts)
+    p32, v32 = _forward(e, sts, engine.EVAL_NET_FP32)
+    p, v = _forward(e, sts, engine.EVAL_NET_BF16)
+    print("trained-like: fp32 max|dp|=%.2e max|dv|=%.2e ; bf16 max|dp|=%.2e max|dv|=%.2e"
+          % (np.abs(p32 - pr).max(), np.abs(v32 - vr).max(), np.abs(p - pr).max(), np.abs(v - vr).max()))
+    assert np.abs(p32 - pr).max() <= 1e-4 and np.abs(v32 - vr).max() <= 1e-4
+    assert np.abs(p - pr).max() <= TOL and np.abs(v - vr).max() <= TOL
+
+
+def test_forward_ragged_batches_are_row_independent(setup):
+    """any batch size (incl. 1, non-multiples of 5 positions per CTA group, > n_slots) gives the same rows"""
+    import engine
+    e, model, sts = setup
+    e.upload_model(model)
+    full_p, full_v = _forward(e, sts[:300], engine.EVAL_NET_BF16)
+    for n in (1, 4, 5, 6, 127, 256, 257):
+        p, v = _forward(e, sts[:n], engine.EVAL_NET_BF16)
+        assert (p == full_p[:n]).all() and (v == full_v[:n]).all()
+    p32, _ = _forward(e, sts[:7], engine.EVAL_NET_FP32)
+    q32, _ = _forward(e, sts[:300], engine.EVAL_NET_FP32)
+    assert (p32 == q32[:7]).all()
+
+
+def test_selfplay_with_network_produces_valid_history(setup):
+    import torch
+    import engine
+    import self_play_cpp
+    e, model, sts = setup
+    e.upload_model(model)
+    h = e.selfplay(16, sims=50, batch=8, seed=3, evaluator=engine.EVAL_NET_BF16)
+    assert (h.lens >= 17).all() and (h.lens <= 81).all()
+    st, cn, z = h.samples()
+    assert (cn.sum(1) == 50).all()                       # sum of root visits == evaluate_count (Q-M4)
+    # every recorded action was legal and visited
+    masks, _ = engine.game_legal_mask(torch.from_numpy(st.view(np.int32)).cuda())
+    masks = masks.cpu().numpy().view(np.uint32)
+    acts = np.concatenate([h.actions[g, :h.lens[g]] for g in range(16)]).astype(np.int64)
+    assert (((masks[np.arange(len(acts)), acts // 27] >> (acts % 27)) & 1) == 1).all()
+    assert (cn[np.arange(len(acts)), acts] > 0).all()
+    legal = np.stack([((masks[:, a // 27] >> (a % 27)) & 1) for a in range(81)], 1).astype(bool)
+    assert (cn[~legal] == 0).all()
+    # reference output format (self_play_cpp.py:34-101)
+    xs, pis, zs = self_play_cpp._history_arrays(e, h)
+    hist = self_play_cpp._to_reference_format(xs, pis, zs)
+    assert len(hist) == h.lens.sum()
+    x, pi, zz = hist[0]
+    assert x.shape == (9, 9, 3) and x.dtype == np.float32 and pi.shape == (81,) and pi.dtype == np.float64
+    assert isinstance(zz, int) and abs(pis.sum(1) - 1).max() < 1e-12
+    assert (x[:, :, 2].sum() == 81) and x[:, :, :2].sum() == 0           # initial position
+
+
+def test_drop_in_play_and_scores_api(setup):
+    import uttt_cpp
+    import pv_mcts_cpp
+    import self_play_cpp
+    e, model, sts = setup
+    s = uttt_cpp.State()
+    sc = pv_mcts_cpp.pv_mcts_scores_cpp(model, s, 1.0, 50, 8)
+    assert sc.dtype == np.float64 and len(sc) == 81 and abs(sc.sum() - 1) < 1e-5
+    sc0 = pv_mcts_cpp.pv_mcts_scores_cpp(model, s, 0, 50, 8)
+    assert sorted(sc0.tolist())[-2:] == [0.0, 1.0]
+    a = pv_mcts_cpp.pv_mcts_action_cpp(model, 1.0)(s)
+    assert 0 <= int(a) < 81
+    np.random.seed(0)
+    hist = self_play_cpp.play(model)
+    assert 17 <= len(hist) <= 81 and hist[0][1].shape == (81,)
+    assert [h[2] for h in hist[:2]] in ([-1, 1], [0, 0])

@@ -1,0 +1,136 @@
+// common.cuh -- shared declarations of libuttt_b200.so (internal).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/uttt_b200.h"
+#include "uttt_rules.cuh"
+
+namespace uttt {
+
+void set_error(const char* fmt, ...);
+
+#define UTTT_CUDA_OK(expr)                                                                   \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::uttt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 1;                                                                        \
+        }                                                                                    \
+    } while (0)
+
+#define UTTT_CHECK(cond, ...)               \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::uttt::set_error(__VA_ARGS__); \
+            return 2;                       \
+        }                                   \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------- network geometry
+constexpr int NET_C = 128;        // DN_FILTERS          dual_network.py:12
+constexpr int NET_BLOCKS = 16;    // DN_RESIDUAL_NUM     dual_network.py:13
+constexpr int NET_LAYERS = 2 * NET_BLOCKS;
+constexpr int NET_CELLS = 81;
+constexpr int NET_ACTIONS = 81;   // DN_OUTPUT_SIZE      dual_network.py:15
+
+// ---------------------------------------------------------------- tree storage
+constexpr int PATH_CAP = 96;      // root + at most 81 plies
+
+enum : int32_t { PHASE_DONE = 0, PHASE_SEARCH = 1, PHASE_PENDING = 2 };
+enum : int32_t { MODE_SEARCH = 0, MODE_SELFPLAY = 1 };
+
+struct alignas(16) TreeCtl {
+    int32_t phase;
+    int32_t sims_left;
+    int32_t n_nodes;
+    int32_t path_len;
+    int32_t pend_k;
+    int32_t nn_row;
+    int32_t n_root;
+    int32_t ply;
+    uint64_t game;      // absolute game id (self-play)
+    int32_t game_idx;   // index into the history buffers
+    int32_t pad;
+};
+
+struct TreeParams {
+    int32_t n_trees, node_cap, sims, batch, mode, flags;
+    PackedState* root;        // [n_trees]
+    PackedState* leaf_state;  // [n_trees]
+    TreeCtl* ctl;             // [n_trees]
+    int32_t* path;            // [n_trees][PATH_CAP]
+    // node SoA, [n_trees][node_cap]
+    int32_t* node_n;
+    float* node_w;
+    float* node_p;
+    uint32_t* node_child;     // index of first child, 0 = unexpanded
+    uint32_t* node_meta;      // (n_children << 8) | action
+    // evaluator queue (rows are compacted with an atomic counter, double-buffered by round parity)
+    PackedState* nn_states;   // [rows]
+    __nv_bfloat16* nn_planes; // [rows][3*81]
+    int32_t* nn_tree;         // [rows]
+    int32_t* nn_k;            // [rows]
+    int32_t* nn_count;        // [2]
+    int32_t parity;
+    const float* policy;      // [(row*row_stride + copy*copy_stride)][81]
+    const float* value;
+    int32_t row_stride, copy_stride;
+    // search outputs
+    int32_t* out_counts;      // [n_trees][81]
+    int32_t* out_n;           // [n_trees]
+    // self-play
+    uint32_t seed;
+    uint64_t game0;
+    int64_t n_games;
+    unsigned long long* counters;  // [0] next game, [1] finished games, [2] plies, [3] sims, [4] evals, [5] overflow flag
+    PackedState* hist_states;      // [n_games][81]
+    uint16_t* hist_counts;         // [n_games][81][81]
+    uint8_t* hist_actions;         // [n_games][81]
+    int32_t* hist_len;             // [n_games]
+    int8_t* hist_final;            // [n_games]
+};
+
+// kernels' host launchers (each returns cudaGetLastError of the launch)
+cudaError_t launch_tree_begin(const TreeParams& p, cudaStream_t s);
+cudaError_t launch_tree_round(const TreeParams& p, cudaStream_t s);
+cudaError_t launch_hash_eval(const PackedState* states, const int32_t* k, const int32_t* count, int max_rows,
+                             float* policy, float* value, int row_stride, int copy_stride, cudaStream_t s);
+cudaError_t launch_scores(const int32_t* counts, const int32_t* n, int n_trees, float temperature,
+                          float* scores, cudaStream_t s);
+cudaError_t launch_boltzman(const float* xs, int n, float temperature, float* out, cudaStream_t s);
+
+// ---------------------------------------------------------------- network
+struct NetWeights {
+    // fp32 path: folded BN (scale into the weights, shift separate); layout [layer][tap][cin][cout]
+    float* conv_in_w;     // [9][3][128]
+    float* conv_in_b;     // [128]
+    float* res_w;         // [32][9][128][128]
+    float* res_b;         // [32][128]
+    // bf16 tensor-core path: [layer][tap][k-panel 16][cout 128][8]  (UMMA canonical K-major, no swizzle)
+    __nv_bfloat16* res_w_bf16;
+    // heads (fp32): policy conv [2][128] + shift[2], fc [81][162] + b; value conv [128] + shift, fc1 [256][81]+b, fc2 [256]+b
+    float* pol_conv_w; float* pol_conv_b; float* pol_fc_w; float* pol_fc_b;
+    float* val_conv_w; float* val_conv_b; float* val_fc1_w; float* val_fc1_b; float* val_fc2_w; float* val_fc2_b;
+    bool loaded;
+};
+
+// trunk input: bf16 planes [rows][3][81]; output: final trunk activations [rows][81][128] (fp32 or bf16)
+cudaError_t launch_conv_input(const NetWeights& w, const __nv_bfloat16* planes, const int32_t* count, int max_rows,
+                              float* out, cudaStream_t s);
+cudaError_t launch_trunk_fp32(const NetWeights& w, const __nv_bfloat16* planes, const int32_t* count, int max_rows,
+                              float* act_a, float* act_b, cudaStream_t s);
+// act: in = conv_input output, out = trunk output (fp32 [rows][81][128]); resid: [ceil(rows/5)][512][128] fp32
+cudaError_t launch_trunk_tc(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* resid,
+                            int n_sm, cudaStream_t s);
+cudaError_t launch_heads(const NetWeights& w, const float* act_f32, const __nv_bfloat16* act_bf16,
+                         const int32_t* count, int max_rows, float* policy, float* value, int row_stride,
+                         cudaStream_t s);
+int trunk_tc_smem_bytes();
+cudaError_t trunk_tc_init();
+
+}  // namespace uttt

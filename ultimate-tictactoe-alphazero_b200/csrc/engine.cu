@@ -1,0 +1,485 @@
+// engine.cu -- host side of libuttt_b200.so: the engine object (HBM arenas for trees, evaluator
+// queues, network weights, history buffers) and the C-ABI entry points for the network forward,
+// the batched search and the self-play loop.
+//
+// Reference call stack replaced:
+//   self_play_cpp.self_play -> play -> pv_mcts_scores_cpp -> uttt_cpp.pv_mcts_scores
+//     -> C++ MCTS -> Python inference callback -> DualNetwork.forward
+// Here every game of a self-play cycle is a slot on the device; one "round" is
+//   tree_round kernel (apply previous evaluation, select next leaf, gather planes)
+//   -> evaluator (trunk + heads kernels, or the hash evaluator)
+// enqueued back to back on one stream with no host synchronisation except a progress check
+// every CHECK_EVERY rounds.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+using namespace uttt;
+
+namespace {
+
+constexpr int CHECK_EVERY = 16;
+constexpr int EV_POOL = CHECK_EVERY * 4;
+
+__global__ void set_int_kernel(int32_t* p, int32_t v) { *p = v; }
+
+template <typename T>
+cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+}  // namespace
+
+struct uttt_engine {
+    uttt_config cfg;
+    int n_sm;
+    int node_cap;
+    cudaStream_t stream;
+    TreeParams tp;          // device pointers (n_trees / mode / sims set per call)
+    float* policy;          // [n_slots*max_batch][81]
+    float* value;           // [n_slots*max_batch]
+    float* scores;          // [n_slots][81]
+    float* act_a;           // [n_slots][81][128] fp32
+    float* act_b;
+    float* tc_resid;        // [groups][512][128] fp32 residual stream of the tensor-core trunk
+    int32_t* fwd_count;     // device int for uttt_net_forward
+    NetWeights w;
+    unsigned long long* h_counters;   // pinned [8]
+    int32_t* h_count;                 // pinned [2]
+    // step-wise search state
+    int s_n_roots, s_sims, s_batch, s_round, s_pending, s_per_copy, s_have_results;
+    // profiling of the last self-play run
+    cudaEvent_t ev[EV_POOL];
+    double prof_ms[4];
+    int64_t prof_launches[4];
+    std::vector<void*> allocs;
+};
+
+namespace {
+
+template <typename T>
+int ealloc(uttt_engine* e, T** p, size_t n) {
+    UTTT_CUDA_OK(dmalloc(p, n ? n : 1));
+    e->allocs.push_back((void*)*p);
+    return 0;
+}
+
+int run_evaluator(uttt_engine* e, int evaluator, const int32_t* count, int max_rows, cudaStream_t s,
+                  cudaEvent_t* ev3 /* optional: [0] before trunk, [1] after trunk, [2] after heads */) {
+    if (evaluator == UTTT_EVAL_HASH) {
+        if (ev3) cudaEventRecord(ev3[0], s);
+        UTTT_CUDA_OK(launch_hash_eval(e->tp.nn_states, e->tp.nn_k, count, max_rows, e->policy, e->value, 1, 0, s));
+        if (ev3) { cudaEventRecord(ev3[1], s); cudaEventRecord(ev3[2], s); }
+        e->prof_launches[1] += 1;
+        return 0;
+    }
+    UTTT_CHECK(e->w.loaded, "network weights not uploaded (uttt_upload_weights)");
+    if (ev3) cudaEventRecord(ev3[0], s);
+    if (evaluator == UTTT_EVAL_NET_FP32) {
+        UTTT_CUDA_OK(launch_trunk_fp32(e->w, e->tp.nn_planes, count, max_rows, e->act_a, e->act_b, s));
+        e->prof_launches[1] += 1 + 2 * NET_BLOCKS;
+    } else if (evaluator == UTTT_EVAL_NET_BF16) {
+        UTTT_CUDA_OK(launch_conv_input(e->w, e->tp.nn_planes, count, max_rows, e->act_a, s));
+        UTTT_CUDA_OK(launch_trunk_tc(e->w, e->act_a, count, max_rows, e->tc_resid, e->n_sm, s));
+        e->prof_launches[1] += 2;
+    } else {
+        UTTT_CHECK(false, "evaluator %d cannot run on the device", evaluator);
+    }
+    if (ev3) cudaEventRecord(ev3[1], s);
+    UTTT_CUDA_OK(launch_heads(e->w, e->act_a, nullptr, count, max_rows, e->policy, e->value, 1, s));
+    e->prof_launches[2] += 1;
+    if (ev3) cudaEventRecord(ev3[2], s);
+    return 0;
+}
+
+int check_search_args(uttt_engine* e, int n_roots, int sims, int batch) {
+    UTTT_CHECK(e != nullptr, "null engine");
+    UTTT_CHECK(n_roots >= 0 && n_roots <= e->cfg.n_slots, "n_roots %d exceeds n_slots %d", n_roots, e->cfg.n_slots);
+    UTTT_CHECK(sims >= 1 && sims <= e->cfg.max_sims, "evaluate_count %d outside [1, max_sims=%d]", sims, e->cfg.max_sims);
+    UTTT_CHECK(batch >= 1 && batch <= e->cfg.max_batch, "batch_size %d outside [1, max_batch=%d]", batch, e->cfg.max_batch);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int uttt_create(const uttt_config* cfg, uttt_engine** out) {
+    UTTT_CHECK(cfg && out, "null argument");
+    UTTT_CHECK(cfg->n_slots >= 1 && cfg->max_sims >= 1 && cfg->max_batch >= 1 && cfg->max_games >= 0,
+               "bad config (n_slots=%d max_sims=%d max_batch=%d)", cfg->n_slots, cfg->max_sims, cfg->max_batch);
+    if (uttt_device_check(cfg->device)) return 1;
+    UTTT_CUDA_OK(cudaSetDevice(cfg->device));
+    uttt_engine* e = new uttt_engine();
+    memset(&e->tp, 0, sizeof(e->tp));
+    memset(&e->w, 0, sizeof(e->w));
+    e->cfg = *cfg;
+    cudaDeviceProp prop;
+    UTTT_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+    e->n_sm = prop.multiProcessorCount;
+    // worst case per tree: root + 81 root children + (sum of k over evaluations <= sims) * 81
+    e->node_cap = 1 + 81 + 81 * cfg->max_sims;
+    UTTT_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    size_t S = (size_t)cfg->n_slots, NC = (size_t)e->node_cap, G = (size_t)cfg->max_games;
+    TreeParams& t = e->tp;
+    t.node_cap = e->node_cap;
+    if (ealloc(e, &t.root, S) || ealloc(e, &t.leaf_state, S) || ealloc(e, &t.ctl, S) ||
+        ealloc(e, &t.path, S * PATH_CAP) || ealloc(e, &t.node_n, S * NC) || ealloc(e, &t.node_w, S * NC) ||
+        ealloc(e, &t.node_p, S * NC) || ealloc(e, &t.node_child, S * NC) || ealloc(e, &t.node_meta, S * NC) ||
+        ealloc(e, &t.nn_states, S) || ealloc(e, &t.nn_planes, S * 243 + 8) || ealloc(e, &t.nn_tree, S) ||
+        ealloc(e, &t.nn_k, S) || ealloc(e, &t.nn_count, 2) || ealloc(e, &t.out_counts, S * 81) ||
+        ealloc(e, &t.out_n, S) || ealloc(e, &t.counters, 8) || ealloc(e, &t.hist_states, G * 81) ||
+        ealloc(e, &t.hist_counts, G * 81 * 81) || ealloc(e, &t.hist_actions, G * 81) || ealloc(e, &t.hist_len, G) ||
+        ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
+        ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
+        ealloc(e, &e->act_a, S * 81 * 128) || ealloc(e, &e->act_b, S * 81 * 128) ||
+        ealloc(e, &e->tc_resid, ((S + 4) / 5) * 512 * 128) || ealloc(e, &e->fwd_count, 1)) {
+        uttt_destroy(e);
+        return 1;
+    }
+    UTTT_CUDA_OK(cudaMemset(t.ctl, 0, S * sizeof(TreeCtl)));
+    UTTT_CUDA_OK(cudaMemset(t.nn_count, 0, 2 * sizeof(int32_t)));
+    UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_counters, 8 * sizeof(unsigned long long)));
+    UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_count, 2 * sizeof(int32_t)));
+    for (int i = 0; i < EV_POOL; i++) UTTT_CUDA_OK(cudaEventCreate(&e->ev[i]));
+    t.policy = e->policy;
+    t.value = e->value;
+    *out = e;
+    return 0;
+}
+
+int uttt_destroy(uttt_engine* e) {
+    if (!e) return 0;
+    cudaSetDevice(e->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : e->allocs) cudaFree(p);
+    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, e->w.pol_conv_w,
+                   e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
+                   e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b};
+    for (float* p : wp) if (p) cudaFree(p);
+    if (e->h_counters) cudaFreeHost(e->h_counters);
+    if (e->h_count) cudaFreeHost(e->h_count);
+    for (int i = 0; i < EV_POOL; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- weights
+// Eval-mode BatchNorm folding: y = gamma*(x-mean)/sqrt(var+eps) + beta = scale*x + shift.
+static void bn_fold(const float* bn, int C, std::vector<float>& scale, std::vector<float>& shift) {
+    scale.resize(C); shift.resize(C);
+    for (int c = 0; c < C; c++) {
+        float g = bn[c], b = bn[C + c], m = bn[2 * C + c], v = bn[3 * C + c];
+        float s = g / sqrtf(v + 1e-5f);
+        scale[c] = s;
+        shift[c] = b - m * s;
+    }
+}
+
+static int to_device(float** dst, const std::vector<float>& v) {
+    if (!*dst) UTTT_CUDA_OK(cudaMalloc((void**)dst, v.size() * sizeof(float)));
+    UTTT_CUDA_OK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
+    UTTT_CHECK(e && w, "null argument");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    auto fetch = [&](const float* p, size_t n, std::vector<float>& v) -> int {
+        v.resize(n);
+        UTTT_CHECK(p != nullptr, "null weight tensor");
+        if (on_device) UTTT_CUDA_OK(cudaMemcpy(v.data(), p, n * sizeof(float), cudaMemcpyDeviceToHost));
+        else memcpy(v.data(), p, n * sizeof(float));
+        return 0;
+    };
+    std::vector<float> ciw, bni, rw, rbn, pcw, pbn, pfw, pfb, vcw, vbn, v1w, v1b, v2w, v2b;
+    if (fetch(w->conv_input_w, 128 * 27, ciw) || fetch(w->bn_input, 4 * 128, bni) ||
+        fetch(w->res_conv_w, (size_t)32 * 128 * 128 * 9, rw) || fetch(w->res_bn, (size_t)32 * 4 * 128, rbn) ||
+        fetch(w->policy_conv_w, 2 * 128, pcw) || fetch(w->policy_bn, 8, pbn) || fetch(w->policy_fc_w, 81 * 162, pfw) ||
+        fetch(w->policy_fc_b, 81, pfb) || fetch(w->value_conv_w, 128, vcw) || fetch(w->value_bn, 4, vbn) ||
+        fetch(w->value_fc1_w, 256 * 81, v1w) || fetch(w->value_fc1_b, 256, v1b) || fetch(w->value_fc2_w, 256, v2w) ||
+        fetch(w->value_fc2_b, 1, v2b))
+        return 1;
+
+    std::vector<float> sc, sh;
+    // conv_input: (128,3,3,3) [co][ci][ky][kx] -> [tap][ci][co]
+    bn_fold(bni.data(), 128, sc, sh);
+    std::vector<float> ci_w(9 * 3 * 128), ci_b(sh);
+    for (int co = 0; co < 128; co++)
+        for (int ci = 0; ci < 3; ci++)
+            for (int tap = 0; tap < 9; tap++)
+                ci_w[(tap * 3 + ci) * 128 + co] = ciw[(co * 3 + ci) * 9 + tap] * sc[co];
+    // residual convs: (32)(128,128,3,3) -> fp32 [layer][tap][ci][co] and bf16 [layer][tap][ci/8][co][ci%8]
+    std::vector<float> r_w((size_t)32 * 9 * 128 * 128), r_b(32 * 128);
+    std::vector<__nv_bfloat16> r_h((size_t)32 * 9 * 128 * 128);
+    for (int l = 0; l < 32; l++) {
+        bn_fold(rbn.data() + (size_t)l * 4 * 128, 128, sc, sh);
+        for (int co = 0; co < 128; co++) {
+            r_b[l * 128 + co] = sh[co];
+            for (int ci = 0; ci < 128; ci++)
+                for (int tap = 0; tap < 9; tap++) {
+                    float v = rw[(((size_t)l * 128 + co) * 128 + ci) * 9 + tap] * sc[co];
+                    r_w[(((size_t)l * 9 + tap) * 128 + ci) * 128 + co] = v;
+                    r_h[((((size_t)l * 9 + tap) * 16 + ci / 8) * 128 + co) * 8 + (ci % 8)] = __float2bfloat16(v);
+                }
+        }
+    }
+    // heads
+    bn_fold(pbn.data(), 2, sc, sh);
+    std::vector<float> pc_w(256), pc_b(sh);
+    for (int j = 0; j < 2; j++)
+        for (int c = 0; c < 128; c++) pc_w[j * 128 + c] = pcw[j * 128 + c] * sc[j];
+    std::vector<float> pf_t(162 * 81);
+    for (int o = 0; o < 81; o++)
+        for (int i = 0; i < 162; i++) pf_t[i * 81 + o] = pfw[o * 162 + i];
+    bn_fold(vbn.data(), 1, sc, sh);
+    std::vector<float> vc_w(128), vc_b(sh);
+    for (int c = 0; c < 128; c++) vc_w[c] = vcw[c] * sc[0];
+    std::vector<float> v1_t(81 * 256);
+    for (int j = 0; j < 256; j++)
+        for (int i = 0; i < 81; i++) v1_t[i * 256 + j] = v1w[j * 81 + i];
+
+    NetWeights& W = e->w;
+    if (to_device(&W.conv_in_w, ci_w) || to_device(&W.conv_in_b, ci_b) || to_device(&W.res_w, r_w) ||
+        to_device(&W.res_b, r_b) || to_device(&W.pol_conv_w, pc_w) || to_device(&W.pol_conv_b, pc_b) ||
+        to_device(&W.pol_fc_w, pf_t) || to_device(&W.pol_fc_b, pfb) || to_device(&W.val_conv_w, vc_w) ||
+        to_device(&W.val_conv_b, vc_b) || to_device(&W.val_fc1_w, v1_t) || to_device(&W.val_fc1_b, v1b) ||
+        to_device(&W.val_fc2_w, v2w) || to_device(&W.val_fc2_b, v2b))
+        return 1;
+    if (!W.res_w_bf16) UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_bf16, r_h.size() * sizeof(__nv_bfloat16)));
+    UTTT_CUDA_OK(cudaMemcpy(W.res_w_bf16, r_h.data(), r_h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    UTTT_CUDA_OK(trunk_tc_init());
+    W.loaded = true;
+    return 0;
+}
+
+int uttt_net_forward(uttt_engine* e, const uint32_t* states_dev, int64_t n, int mode, float* policy_dev,
+                     float* value_dev, void* stream) {
+    UTTT_CHECK(e && (n == 0 || (states_dev && policy_dev && value_dev)), "null argument");
+    UTTT_CHECK(mode == UTTT_EVAL_NET_BF16 || mode == UTTT_EVAL_NET_FP32, "mode must be UTTT_EVAL_NET_BF16 or _FP32");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int64_t off = 0; off < n; off += e->cfg.n_slots) {
+        int m = (int)((n - off < e->cfg.n_slots) ? (n - off) : e->cfg.n_slots);
+        if (uttt_game_gather_planes(states_dev + off * 8, e->tp.nn_planes, m, s)) return 1;
+        set_int_kernel<<<1, 1, 0, s>>>(e->fwd_count, m);
+        if (run_evaluator(e, mode, e->fwd_count, m, s, nullptr)) return 1;
+        UTTT_CUDA_OK(cudaMemcpyAsync(policy_dev + off * 81, e->policy, (size_t)m * 81 * sizeof(float),
+                                     cudaMemcpyDeviceToDevice, s));
+        UTTT_CUDA_OK(cudaMemcpyAsync(value_dev + off, e->value, (size_t)m * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- search
+int uttt_mcts_begin(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int32_t sims, int32_t batch) {
+    if (check_search_args(e, n_roots, sims, batch)) return 1;
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    TreeParams& t = e->tp;
+    t.n_trees = n_roots; t.sims = sims; t.batch = batch; t.mode = MODE_SEARCH; t.flags = 0;
+    t.parity = 0; t.row_stride = 1; t.copy_stride = 0;
+    e->s_n_roots = n_roots; e->s_sims = sims; e->s_batch = batch; e->s_round = 0; e->s_pending = 0;
+    e->s_per_copy = 0; e->s_have_results = 0;
+    if (n_roots == 0) return 0;
+    UTTT_CUDA_OK(cudaMemcpyAsync(t.root, roots, (size_t)n_roots * 32, cudaMemcpyHostToDevice, e->stream));
+    UTTT_CUDA_OK(cudaMemsetAsync(t.counters, 0, 8 * sizeof(unsigned long long), e->stream));
+    UTTT_CUDA_OK(launch_tree_begin(t, e->stream));
+    return 0;
+}
+
+int uttt_mcts_advance(uttt_engine* e, int32_t* n_pending) {
+    UTTT_CHECK(e && n_pending, "null argument");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    TreeParams& t = e->tp;
+    if (e->s_n_roots == 0) { *n_pending = 0; return 0; }
+    UTTT_CHECK(e->s_pending == 0 || e->s_have_results, "pending leaves have no results yet (uttt_mcts_put_results)");
+    t.parity = e->s_round & 1;
+    UTTT_CUDA_OK(launch_tree_round(t, e->stream));
+    UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + t.parity, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                 e->stream));
+    UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+    UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
+    e->s_pending = e->h_count[0];
+    e->s_have_results = 0;
+    e->s_round++;
+    *n_pending = e->s_pending;
+    return 0;
+}
+
+int uttt_mcts_get_leaves(uttt_engine* e, uint32_t* states, int32_t* k, int32_t* tree) {
+    UTTT_CHECK(e, "null engine");
+    int n = e->s_pending;
+    if (n == 0) return 0;
+    if (states) UTTT_CUDA_OK(cudaMemcpyAsync(states, e->tp.nn_states, (size_t)n * 32, cudaMemcpyDeviceToHost, e->stream));
+    if (k) UTTT_CUDA_OK(cudaMemcpyAsync(k, e->tp.nn_k, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (tree) UTTT_CUDA_OK(cudaMemcpyAsync(tree, e->tp.nn_tree, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int uttt_mcts_put_results(uttt_engine* e, const float* policy, const float* value, int per_copy) {
+    UTTT_CHECK(e && policy && value, "null argument");
+    int n = e->s_pending;
+    size_t rows = per_copy ? (size_t)n * e->cfg.max_batch : (size_t)n;
+    UTTT_CUDA_OK(cudaMemcpyAsync(e->policy, policy, rows * 81 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    UTTT_CUDA_OK(cudaMemcpyAsync(e->value, value, rows * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    e->tp.row_stride = per_copy ? e->cfg.max_batch : 1;
+    e->tp.copy_stride = per_copy ? 1 : 0;
+    e->s_have_results = 1;
+    return 0;
+}
+
+int uttt_mcts_finish(uttt_engine* e, float temperature, float* scores, int32_t* counts, int32_t* n_scores) {
+    UTTT_CHECK(e, "null engine");
+    int n = e->s_n_roots;
+    if (n == 0) return 0;
+    UTTT_CUDA_OK(launch_scores(e->tp.out_counts, e->tp.out_n, n, temperature, e->scores, e->stream));
+    if (scores) UTTT_CUDA_OK(cudaMemcpyAsync(scores, e->scores, (size_t)n * 81 * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (counts) UTTT_CUDA_OK(cudaMemcpyAsync(counts, e->tp.out_counts, (size_t)n * 81 * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (n_scores) UTTT_CUDA_OK(cudaMemcpyAsync(n_scores, e->tp.out_n, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+    UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int32_t sims, int32_t batch,
+                     float temperature, int32_t evaluator, float* scores, int32_t* counts, int32_t* n_scores) {
+    UTTT_CHECK(evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_FP32 || evaluator == UTTT_EVAL_HASH,
+               "uttt_mcts_search needs a device evaluator; use the step-wise calls for UTTT_EVAL_HOST");
+    if (uttt_mcts_begin(e, roots, n_roots, sims, batch)) return 1;
+    if (n_roots == 0) return 0;
+    TreeParams& t = e->tp;
+    // rounds are enqueued without host synchronisation; the tree kernel ignores finished trees.
+    // Upper bound on rounds: every round retires >= 1 simulation of every unfinished tree.
+    int max_rounds = sims + 1;
+    int r = 0;
+    while (r < max_rounds) {
+        int stop = (r + CHECK_EVERY < max_rounds) ? r + CHECK_EVERY : max_rounds;
+        for (; r < stop; r++) {
+            t.parity = r & 1;
+            UTTT_CUDA_OK(launch_tree_round(t, e->stream));
+            if (run_evaluator(e, evaluator, t.nn_count + t.parity, n_roots, e->stream, nullptr)) return 1;
+        }
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + ((r - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost,
+                                     e->stream));
+        UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+        if (e->h_count[0] == 0) break;      // nothing was queued in the last round: every tree is done
+    }
+    UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
+    UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+    UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
+    e->s_n_roots = n_roots;
+    return uttt_mcts_finish(e, temperature, scores, counts, n_scores);
+}
+
+int uttt_boltzman(const float* xs, int32_t n, float temperature, float* out) {
+    UTTT_CHECK(xs && out && n >= 0, "bad argument");
+    UTTT_CHECK(temperature != 0.0f, "temperature must be non-zero");
+    if (n == 0) return 0;
+    float *dx = nullptr, *dy = nullptr;
+    UTTT_CUDA_OK(cudaMalloc((void**)&dx, n * sizeof(float)));
+    UTTT_CUDA_OK(cudaMalloc((void**)&dy, n * sizeof(float)));
+    UTTT_CUDA_OK(cudaMemcpy(dx, xs, n * sizeof(float), cudaMemcpyHostToDevice));
+    UTTT_CUDA_OK(launch_boltzman(dx, n, temperature, dy, 0));
+    UTTT_CUDA_OK(cudaMemcpy(out, dy, n * sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(dx);
+    cudaFree(dy);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------- self-play
+int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, int32_t sims, int32_t batch,
+                             uint32_t seed, int32_t evaluator, int32_t flags, int64_t* stats, void* stream) {
+    UTTT_CHECK(e != nullptr, "null engine");
+    UTTT_CHECK(n_games >= 0 && n_games <= e->cfg.max_games, "n_games %lld exceeds max_games %lld", (long long)n_games,
+               (long long)e->cfg.max_games);
+    UTTT_CHECK(evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_FP32 || evaluator == UTTT_EVAL_HASH,
+               "self-play needs a device evaluator");
+    int n_trees = (int)((n_games < e->cfg.n_slots) ? n_games : e->cfg.n_slots);
+    if (check_search_args(e, n_trees, sims, batch)) return 1;
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    for (int i = 0; i < 4; i++) { e->prof_ms[i] = 0.0; e->prof_launches[i] = 0; }
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (n_games == 0) return 0;
+    TreeParams& t = e->tp;
+    t.n_trees = n_trees; t.sims = sims; t.batch = batch; t.mode = MODE_SELFPLAY; t.flags = flags;
+    t.parity = 0; t.row_stride = 1; t.copy_stride = 0;
+    t.seed = seed; t.game0 = game0; t.n_games = n_games;
+    UTTT_CUDA_OK(cudaMemsetAsync(t.counters, 0, 8 * sizeof(unsigned long long), s));
+    UTTT_CUDA_OK(cudaMemsetAsync(t.hist_len, 0, (size_t)n_games * sizeof(int32_t), s));
+    UTTT_CUDA_OK(launch_tree_begin(t, s));
+    e->prof_launches[0] += 1;
+    // every round retires >= 1 simulation of every live slot: hard upper bound on rounds
+    int64_t waves = (n_games + n_trees - 1) / n_trees;
+    int64_t max_rounds = waves * 82 * (int64_t)(sims + 1) + CHECK_EVERY;
+    int64_t r = 0;
+    bool done = false;
+    while (!done && r < max_rounds) {
+        int in_window = 0;
+        for (; in_window < CHECK_EVERY; in_window++, r++) {
+            cudaEvent_t* ev = e->ev + 4 * in_window;
+            t.parity = (int)(r & 1);
+            cudaEventRecord(ev[0], s);
+            UTTT_CUDA_OK(launch_tree_round(t, s));
+            e->prof_launches[0] += 1;
+            if (run_evaluator(e, evaluator, t.nn_count + t.parity, n_trees, s, ev + 1)) return 1;
+        }
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+        UTTT_CUDA_OK(cudaStreamSynchronize(s));
+        for (int i = 0; i < in_window; i++) {
+            float ms = 0.f;
+            cudaEvent_t* ev = e->ev + 4 * i;
+            cudaEventElapsedTime(&ms, ev[0], ev[1]); e->prof_ms[0] += ms;
+            cudaEventElapsedTime(&ms, ev[1], ev[2]); e->prof_ms[1] += ms;
+            cudaEventElapsedTime(&ms, ev[2], ev[3]); e->prof_ms[2] += ms;
+            cudaEventElapsedTime(&ms, ev[0], ev[3]); e->prof_ms[3] += ms;
+        }
+        UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
+        done = (int64_t)e->h_counters[1] >= n_games;
+    }
+    UTTT_CHECK(done, "self-play did not finish within %lld rounds", (long long)max_rounds);
+    e->prof_launches[3] = e->prof_launches[0] + e->prof_launches[1] + e->prof_launches[2];
+    if (stats) {
+        stats[0] = (int64_t)e->h_counters[2];
+        stats[1] = (int64_t)e->h_counters[3];
+        stats[2] = (int64_t)e->h_counters[4];
+        stats[3] = r;
+    }
+    return 0;
+}
+
+int uttt_selfplay_fetch(uttt_engine* e, int64_t n_games, uint32_t* hist_states, uint16_t* hist_counts,
+                        uint8_t* hist_actions, int32_t* hist_len, int8_t* hist_final) {
+    UTTT_CHECK(e && n_games <= e->cfg.max_games, "bad argument");
+    if (n_games <= 0) return 0;
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    size_t G = (size_t)n_games;
+    cudaStream_t s = e->stream;
+    const TreeParams& t = e->tp;
+    if (hist_states) UTTT_CUDA_OK(cudaMemcpyAsync(hist_states, t.hist_states, G * 81 * 32, cudaMemcpyDeviceToHost, s));
+    if (hist_counts) UTTT_CUDA_OK(cudaMemcpyAsync(hist_counts, t.hist_counts, G * 81 * 81 * 2, cudaMemcpyDeviceToHost, s));
+    if (hist_actions) UTTT_CUDA_OK(cudaMemcpyAsync(hist_actions, t.hist_actions, G * 81, cudaMemcpyDeviceToHost, s));
+    if (hist_len) UTTT_CUDA_OK(cudaMemcpyAsync(hist_len, t.hist_len, G * 4, cudaMemcpyDeviceToHost, s));
+    if (hist_final) UTTT_CUDA_OK(cudaMemcpyAsync(hist_final, t.hist_final, G, cudaMemcpyDeviceToHost, s));
+    UTTT_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int uttt_selfplay_run(uttt_engine* e, int64_t n_games, uint64_t game0, int32_t sims, int32_t batch, uint32_t seed,
+                      int32_t evaluator, int32_t flags, uint32_t* hist_states, uint16_t* hist_counts,
+                      uint8_t* hist_actions, int32_t* hist_len, int8_t* hist_final, int64_t* stats) {
+    if (uttt_selfplay_run_device(e, n_games, game0, sims, batch, seed, evaluator, flags, stats, nullptr)) return 1;
+    return uttt_selfplay_fetch(e, n_games, hist_states, hist_counts, hist_actions, hist_len, hist_final);
+}
+
+int uttt_last_run_profile(uttt_engine* e, int kind, double* ms_out, int64_t* launches_out) {
+    UTTT_CHECK(e && kind >= 0 && kind < 4, "bad argument");
+    if (ms_out) *ms_out = e->prof_ms[kind];
+    if (launches_out) *launches_out = e->prof_launches[kind];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,331 @@
+// net_tc.cu -- the residual trunk of DualNetwork (dual_network.py:28-45,97-99: 16 blocks x 2
+// 3x3 convolutions, 128 -> 128 channels, BatchNorm + ReLU + skip) as ONE persistent sm_100a kernel:
+// tcgen05.mma implicit GEMM with the activations resident in shared memory for all 32 layers.
+//
+// Mapping (per CTA, one CTA per SM, persistent over groups of 5 positions):
+//   * GEMM rows: each position occupies 100 rows of a padded row space, index = 10*r + c
+//     (r,c in 0..8; column 9 and the 10-row gap after row 8 are zero padding), so the 3x3 tap
+//     (dy,dx) is a constant row shift of 10*dy + dx and the zero rows supply the halo.
+//     5 positions = 500 rows = 4 MMA tiles of M = 128 (81 % of the issued rows are real cells).
+//   * A operand (activations, bf16): shared memory, canonical K-major NO-swizzle layout stored as
+//     16 channel panels [panel = ci/8][row][8 ci]: a core matrix (8 rows x 16 B) is 128 contiguous
+//     bytes for ANY starting row, so a tap shift is just a different descriptor start address
+//     (SBO = 128 B between 8-row groups, LBO = panel stride between the two K halves).
+//   * B operand (weights, bf16, BN scale folded): pre-packed in HBM in exactly the shared-memory
+//     image [layer][tap][ci/8][co][ci%8]; streamed by one elected thread with bulk async copies
+//     (cp.async.bulk -> UBLKCP, mbarrier complete_tx) through a 5-stage ring of 16 KiB half-taps.
+//     Each stage feeds 16 MMAs (4 tiles x 4 K-steps), i.e. weights are re-used across the 4 tiles.
+//   * D accumulators: 4 x (128 lanes x 128 fp32 columns) = all 512 TMEM columns.
+//   * Epilogue (16 warps, one TMEM lane quarter of one tile each): tcgen05.ld -> +shift (+skip)
+//     -> ReLU -> zero the padding rows -> bf16 -> back into the SAME shared-memory buffer in place
+//     (all MMAs of the layer have completed).  The fp32 skip connection lives in HBM/L2, written
+//     and re-read by the same thread; only conv_input's output and the last block's output touch
+//     HBM otherwise.
+//
+// Warp roles: warps 0-15 epilogue, warp 16 weight producer, warp 17 MMA issuer + TMEM owner.
+#include "common.cuh"
+
+namespace uttt {
+
+constexpr int TC_P = 5;                       // positions per group
+constexpr int TC_POS_ROWS = 100;              // padded rows per position
+constexpr int TC_TILES = 4;
+constexpr int TC_M = 128 * TC_TILES;          // 512 GEMM rows per group
+constexpr int TC_LEAD = 11;                   // zero rows before row 0 (largest negative shift)
+constexpr int TC_AROWS = 536;                 // >= TC_LEAD + 512 + 11
+constexpr int TC_PANEL_BYTES = TC_AROWS * 16; // one 8-channel panel
+constexpr int TC_A_BYTES = 16 * TC_PANEL_BYTES;
+constexpr int TC_STAGE_BYTES = 16384;         // half a tap: 64 ci x 128 co bf16
+constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES_PER_LAYER = 18;
+constexpr int TC_BAR_OFF = TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES;
+constexpr int TC_SMEM_BYTES = TC_BAR_OFF + 256;
+constexpr int TC_THREADS = 18 * 32;
+constexpr int TC_EPI_WARPS = 16;
+
+// instruction descriptor (kind::f16): D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A and B, N=128, M=128
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug must trap instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; it++) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((it & 1023u) == 1023u) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) {
+                printf("uttt trunk_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                       threadIdx.x, bar, parity);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
+                const float* __restrict__ bias,         // [32][128]
+                float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
+                float* resid,                           // [groups][512][128] fp32 skip connection
+                const int32_t* __restrict__ count) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_pos = *count;
+    const int n_groups = (n_pos + TC_P - 1) / TC_P;
+    if ((int)blockIdx.x >= n_groups) return;
+
+    uint8_t* sA = smem;
+    const uint32_t sA_u = smem_u32(sA);
+    const uint32_t sB_u = sA_u + TC_A_BYTES;
+    const uint32_t bar_u = sA_u + TC_BAR_OFF;
+    // barriers: full[5] @0, empty[5] @40, accum_full @80, act_ready @88; tmem base holder @96
+    const uint32_t bar_full = bar_u, bar_empty = bar_u + 8 * TC_STAGES, bar_accum = bar_u + 16 * TC_STAGES,
+                   bar_act = bar_u + 16 * TC_STAGES + 8;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + TC_BAR_OFF + 16 * TC_STAGES + 16);
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+        mbar_init(bar_accum, 1);
+        mbar_init(bar_act, TC_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 17) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // zero the whole activation buffer once: lead/tail margins and padding rows stay zero forever
+    for (int i = threadIdx.x; i < TC_A_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    int iter = 0;
+    for (int g = blockIdx.x; g < n_groups; g += gridDim.x, iter++) {
+        if (warp < TC_EPI_WARPS) {
+            // ================= epilogue warps: one GEMM row (TMEM lane) per thread =================
+            const int tile = warp >> 2, quarter = warp & 3;
+            const int m = tile * 128 + quarter * 32 + lane;
+            const int pos = m / TC_POS_ROWS, idx = m - pos * TC_POS_ROWS;
+            const int r = idx / 10, c = idx - 10 * r;
+            const int gpos = g * TC_P + pos;
+            const bool valid = (pos < TC_P) && (r < 9) && (c < 9) && (gpos < n_pos);
+            float* arow = act + ((size_t)gpos * 81 + (size_t)(r * 9 + c)) * 128;
+            float* rrow = resid + ((size_t)g * TC_M + (size_t)m) * 128;
+            uint8_t* srow = sA + (size_t)(TC_LEAD + m) * 16;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile * 128);
+
+            // prologue: conv_input output -> skip buffer (fp32) + bf16 A operand of layer 0
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ch++) {
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float4 x = valid ? reinterpret_cast<const float4*>(arow + ch * 32)[j] : make_float4(0, 0, 0, 0);
+                    v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+                    if (valid) reinterpret_cast<float4*>(rrow + ch * 32)[j] = x;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                          pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                    *reinterpret_cast<uint4*>(srow + (size_t)(ch * 4 + j) * TC_PANEL_BYTES) = pk;
+                }
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_act);
+
+#pragma unroll 1
+            for (int layer = 0; layer < NET_LAYERS; layer++) {
+                mbar_wait(bar_accum, (uint32_t)((iter * NET_LAYERS + layer) & 1));
+                tc_fence_after();
+                const bool second = (layer & 1) != 0;          // conv2 of a block: add the skip connection
+                const bool last = (layer == NET_LAYERS - 1);
+                const float* bl = bias + layer * 128;
+#pragma unroll 1
+                for (int ch = 0; ch < 4; ch++) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 32) + j);
+                        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                    }
+                    if (second && valid) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 x = reinterpret_cast<const float4*>(rrow + ch * 32)[j];
+                            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = valid ? fmaxf(v[j], 0.0f) : 0.0f;
+                    if (second && valid) {
+                        float* dst = last ? arow : rrow;
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            reinterpret_cast<float4*>(dst + ch * 32)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                    if (!last) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(srow + (size_t)(ch * 4 + j) * TC_PANEL_BYTES) = pk;
+                        }
+                    }
+                }
+                if (!last) {
+                    fence_async_smem();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_act);
+                }
+            }
+            tc_fence_before();
+        } else if (warp == 16) {
+            // ================= weight producer =================
+#pragma unroll 1
+            for (int n = 0; n < NET_LAYERS * TC_STAGES_PER_LAYER; n++) {
+                const int gn = iter * NET_LAYERS * TC_STAGES_PER_LAYER + n;
+                const int stage = gn % TC_STAGES;
+                const uint32_t par = (uint32_t)((gn / TC_STAGES) & 1);
+                mbar_wait(bar_empty + 8 * stage, par ^ 1u);
+                if (lane == 0) {
+                    mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
+                    bulk_g2s(sB_u + stage * TC_STAGE_BYTES, wq + (size_t)n * (TC_STAGE_BYTES / 2), TC_STAGE_BYTES,
+                             bar_full + 8 * stage);
+                }
+                __syncwarp();
+            }
+        } else {
+            // ================= MMA issuer (one elected lane) =================
+#pragma unroll 1
+            for (int layer = 0; layer < NET_LAYERS; layer++) {
+                mbar_wait(bar_act, (uint32_t)((iter * NET_LAYERS + layer) & 1));
+                tc_fence_after();
+#pragma unroll 1
+                for (int s = 0; s < TC_STAGES_PER_LAYER; s++) {
+                    const int gn = (iter * NET_LAYERS + layer) * TC_STAGES_PER_LAYER + s;
+                    const int stage = gn % TC_STAGES;
+                    const uint32_t par = (uint32_t)((gn / TC_STAGES) & 1);
+                    mbar_wait(bar_full + 8 * stage, par);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const int tap = s >> 1, half = s & 1;
+                        const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
+#pragma unroll
+                        for (int tile = 0; tile < TC_TILES; tile++) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ks++) {
+                                const int kg = half * 4 + ks;
+                                const uint32_t a_addr = sA_u + (uint32_t)(2 * kg) * TC_PANEL_BYTES +
+                                                        (uint32_t)(TC_LEAD + tile * 128 + shift) * 16u;
+                                const uint32_t b_addr = sB_u + (uint32_t)stage * TC_STAGE_BYTES + (uint32_t)ks * 4096u;
+                                umma_bf16(tmem_base + (uint32_t)(tile * 128), make_desc(a_addr, TC_PANEL_BYTES, 128),
+                                          make_desc(b_addr, 2048, 128), TC_IDESC, (uint32_t)((s | ks) != 0));
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * stage);          // frees the weight stage when the MMAs retire
+                        if (s == TC_STAGES_PER_LAYER - 1) umma_commit(bar_accum);   // accumulators complete
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+int trunk_tc_smem_bytes() { return TC_SMEM_BYTES; }
+
+cudaError_t trunk_tc_init() {
+    return cudaFuncSetAttribute(trunk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+}
+
+cudaError_t launch_trunk_tc(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* resid,
+                            int n_sm, cudaStream_t s) {
+    int max_groups = (max_rows + TC_P - 1) / TC_P;
+    int grid = max_groups < n_sm ? max_groups : n_sm;
+    if (grid < 1) grid = 1;
+    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.res_b, act, resid, count);
+    return cudaGetLastError();
+}
+
+}  // namespace uttt

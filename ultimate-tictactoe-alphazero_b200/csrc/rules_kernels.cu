@@ -1,0 +1,297 @@
+// rules_kernels.cu -- bitboard rules kernels over arrays of packed states in HBM, and the
+// host-side single-state helpers behind the `uttt_cpp.State` shim.
+//
+// Replaces UTTT::State (cpp/uttt_game.cpp:9-280).  All kernels are HBM-bound integer/byte work:
+// one thread per 32-byte state, two 128-bit loads / stores per state, fully coalesced
+// (a warp touches 1 KiB of contiguous states); grids are sized from n, no shared memory needed.
+#include <stdarg.h>
+#include <string.h>
+
+#include <string>
+
+#include "common.cuh"
+
+namespace uttt {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+__device__ __forceinline__ PackedState load_state(const PackedState* p) {
+    PackedState s;
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    s.w[0] = a.x; s.w[1] = a.y; s.w[2] = a.z; s.w[3] = a.w;
+    s.w[4] = b.x; s.w[5] = b.y; s.w[6] = b.z; s.w[7] = b.w;
+    return s;
+}
+__device__ __forceinline__ void store_state(PackedState* p, const PackedState& s) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(s.w[0], s.w[1], s.w[2], s.w[3]);
+    q[1] = make_uint4(s.w[4], s.w[5], s.w[6], s.w[7]);
+}
+
+// cpp/uttt_game.cpp:97-145
+__global__ void __launch_bounds__(256) step_kernel(const PackedState* __restrict__ in, const int32_t* __restrict__ act,
+                                                   PackedState* __restrict__ out, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PackedState s = load_state(in + i), o;
+    next_state(s, __ldg(act + i), o);
+    store_state(out + i, o);
+}
+
+// cpp/uttt_game.cpp:77-89,148-191
+__global__ void __launch_bounds__(256) legal_kernel(const PackedState* __restrict__ in, uint4* __restrict__ masks,
+                                                    uint8_t* __restrict__ status, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PackedState s = load_state(in + i);
+    uint32_t lm[3];
+    int cnt = legal_mask(s, lm);
+    masks[i] = make_uint4(lm[0], lm[1], lm[2], (uint32_t)cnt);
+    if (status) status[i] = (uint8_t)status_of(s, cnt);
+}
+
+// cpp/uttt_game.cpp:244-280: float HWC (9,9,3); one thread per output element -> coalesced stores,
+// the 32-byte state is re-read through L1 by the 243 threads that share it.
+__global__ void __launch_bounds__(256) encode_kernel(const PackedState* __restrict__ in, float* __restrict__ planes,
+                                                     int64_t n) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 243) return;
+    int64_t i = idx / 243;
+    int e = (int)(idx - i * 243);
+    int cell = e / 3, ch = e - 3 * cell;
+    int a = action_of_rc(cell / 9, cell % 9);
+    PackedState s = load_state(in + i);
+    bool v;
+    if (ch == 0) v = stone_me(s, a);
+    else if (ch == 1) v = stone_opp(s, a);
+    else {
+        uint32_t lm[3];
+        legal_mask(s, lm);
+        v = legal_bit(lm, a);
+    }
+    planes[idx] = v ? 1.0f : 0.0f;
+}
+
+// leaf gather (pv_mcts_cpp.py:47-60): bf16 CHW (3,9,9) rows of the network's input batch
+__global__ void __launch_bounds__(256) gather_planes_kernel(const PackedState* __restrict__ in,
+                                                            __nv_bfloat16* __restrict__ planes, int64_t n) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * 243) return;
+    int64_t i = idx / 243;
+    int e = (int)(idx - i * 243);
+    int ch = e / 81, cell = e - 81 * ch;
+    int a = action_of_rc(cell / 9, cell % 9);
+    PackedState s = load_state(in + i);
+    bool v;
+    if (ch == 0) v = stone_me(s, a);
+    else if (ch == 1) v = stone_opp(s, a);
+    else {
+        uint32_t lm[3];
+        legal_mask(s, lm);
+        v = legal_bit(lm, a);
+    }
+    planes[idx] = __float2bfloat16(v ? 1.0f : 0.0f);
+}
+
+// Whole random games with the state in registers: HBM traffic is 16 B out per game, the kernel is
+// integer-issue bound.  One thread per game (config 2 of BASELINE.json: 2^20 concurrent playouts).
+__global__ void __launch_bounds__(128) playout_kernel(uint32_t seed, uint64_t game0, int64_t n,
+                                                      uint64_t* __restrict__ digests, int32_t* __restrict__ plies,
+                                                      int32_t* __restrict__ results) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t game = game0 + (uint64_t)i;
+    PackedState s;
+    init_state(s);
+    uint64_t h = 0xCBF29CE484222325ull;
+    int t = 0;
+    for (;;) {
+        uint32_t lm[3];
+        int cnt = legal_mask(s, lm);      // 0 when the mover has already lost
+        if (cnt == 0) break;
+        Philox4 r = philox4x32(seed, 0u, (uint32_t)game, (uint32_t)(game >> 32), (uint32_t)t, 0u);
+        int a = nth_legal(lm, (int)(r.x % (uint32_t)cnt));
+        h = fnv64(h, (uint32_t)a);
+        h = fnv64(h, lm[0]); h = fnv64(h, lm[1]); h = fnv64(h, lm[2]);
+        h = fnv64(h, s.w[6]);
+        PackedState o;
+        next_state(s, a, o);
+        s = o;
+        t++;
+    }
+    bool lose = is_lose(s);
+#pragma unroll
+    for (int k = 0; k < 7; k++) h = fnv64(h, s.w[k]);
+    h = fnv64(h, lose ? 1u : 2u);
+    digests[i] = h;
+    plies[i] = t;
+    results[i] = lose ? (is_first_player(s) ? 2 : 1) : 0;
+}
+
+}  // namespace uttt
+
+using namespace uttt;
+
+extern "C" {
+
+const char* uttt_last_error(void) { return g_err; }
+int uttt_abi_version(void) { return UTTT_ABI_VERSION; }
+
+int uttt_device_check(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        set_error("no CUDA device visible: libuttt_b200 has no CPU fallback");
+        return 1;
+    }
+    UTTT_CHECK(device >= 0 && device < n, "device %d out of range (%d visible)", device, n);
+    cudaDeviceProp p;
+    UTTT_CUDA_OK(cudaGetDeviceProperties(&p, device));
+    UTTT_CHECK(p.major == 10, "device %d is sm_%d%d; this library is built for sm_100a only", device, p.major, p.minor);
+    return 0;
+}
+
+// ---- host single-state helpers -------------------------------------------------------------
+int uttt_state_init(uint32_t* state) {
+    memset(state, 0, 32);
+    return 0;
+}
+
+int uttt_state_next(const uint32_t* state, int action, uint32_t* out) {
+    UTTT_CHECK(action >= 0 && action < 81, "action %d out of range [0,81)", action);
+    PackedState s, o;
+    memcpy(s.w, state, 32);
+    next_state(s, action, o);
+    memcpy(out, o.w, 32);
+    return 0;
+}
+
+int uttt_state_legal_actions(const uint32_t* state, int32_t* out81, int* n_out) {
+    PackedState s;
+    memcpy(s.w, state, 32);
+    uint32_t lm[3];
+    int n = legal_mask(s, lm), k = 0;
+    for (int a = 0; a < 81; a++)
+        if (legal_bit(lm, a)) out81[k++] = a;
+    *n_out = n;
+    return 0;
+}
+
+int uttt_state_flags(const uint32_t* state, int* flags_out) {
+    PackedState s;
+    memcpy(s.w, state, 32);
+    uint32_t lm[3];
+    int n = legal_mask(s, lm);
+    bool lose = is_lose(s), draw = !lose && n == 0;
+    *flags_out = (lose ? 1 : 0) | (draw ? 2 : 0) | ((lose || draw) ? 4 : 0) | (is_first_player(s) ? 8 : 0);
+    return 0;
+}
+
+int uttt_state_encode(const uint32_t* state, float* out243) {
+    PackedState s;
+    memcpy(s.w, state, 32);
+    uint32_t lm[3];
+    legal_mask(s, lm);
+    for (int R = 0; R < 9; R++)
+        for (int C = 0; C < 9; C++) {
+            int a = action_of_rc(R, C);
+            float* o = out243 + (R * 9 + C) * 3;
+            o[0] = stone_me(s, a) ? 1.0f : 0.0f;
+            o[1] = stone_opp(s, a) ? 1.0f : 0.0f;
+            o[2] = legal_bit(lm, a) ? 1.0f : 0.0f;
+        }
+    return 0;
+}
+
+// Debug rendering, same text as cpp/uttt_game.cpp:194-241.
+int uttt_state_to_string(const uint32_t* state, char* buf, int cap, int* len_out) {
+    PackedState s;
+    memcpy(s.w, state, 32);
+    const char* ox = is_first_player(s) ? "ox" : "xo";
+    std::string out;
+    for (int big_r = 0; big_r < 3; big_r++) {
+        for (int sub_r = 0; sub_r < 3; sub_r++) {
+            for (int big_c = 0; big_c < 3; big_c++) {
+                int b = big_r * 3 + big_c;
+                for (int sub_c = 0; sub_c < 3; sub_c++) {
+                    int a = b * 9 + sub_r * 3 + sub_c;
+                    out += stone_me(s, a) ? ox[0] : (stone_opp(s, a) ? ox[1] : '-');
+                    out += ' ';
+                }
+                if (big_c < 2) out += "| ";
+            }
+            out += '\n';
+        }
+        if (big_r < 2) out += "---------------------\n";
+    }
+    out += "\nMain Board Status:\n";
+    uint32_t M = main_me(s), E = main_opp(s);
+    for (int b = 0; b < 9; b++) {
+        bool m = (M >> b) & 1u, e = (E >> b) & 1u;
+        out += (m && e) ? 'D' : (m ? ox[0] : (e ? ox[1] : '.'));
+        if (b % 3 == 2) out += '\n';
+    }
+    out += "Next Player: ";
+    out += ox[0];
+    out += "\nActive Board: ";
+    int act = active_board(s);
+    out += (act < 0) ? std::string("Any") : std::to_string(act);
+    out += '\n';
+    if (len_out) *len_out = (int)out.size();
+    if (buf && cap > 0) {
+        int m = (int)out.size() < cap - 1 ? (int)out.size() : cap - 1;
+        memcpy(buf, out.data(), (size_t)m);
+        buf[m] = 0;
+    }
+    return 0;
+}
+
+// ---- device batch rules --------------------------------------------------------------------
+int uttt_game_step(const uint32_t* states, const int32_t* actions, uint32_t* out, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    step_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((const PackedState*)states, actions,
+                                                                      (PackedState*)out, n);
+    UTTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int uttt_game_legal_mask(const uint32_t* states, uint32_t* masks, uint8_t* status, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    legal_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((const PackedState*)states, (uint4*)masks,
+                                                                       status, n);
+    UTTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int uttt_game_encode(const uint32_t* states, float* planes, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    encode_kernel<<<ceil_div(n * 243, 256), 256, 0, (cudaStream_t)stream>>>((const PackedState*)states, planes, n);
+    UTTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int uttt_game_gather_planes(const uint32_t* states, void* planes, int64_t n, void* stream) {
+    if (n <= 0) return 0;
+    gather_planes_kernel<<<ceil_div(n * 243, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const PackedState*)states, (__nv_bfloat16*)planes, n);
+    UTTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int uttt_game_playout(uint32_t seed, uint64_t game0, int64_t n, uint64_t* digests, int32_t* plies,
+                      int32_t* results, void* stream) {
+    if (n <= 0) return 0;
+    playout_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(seed, game0, n, digests, plies, results);
+    UTTT_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,450 @@
+// tree_kernels.cu -- PUCT search over structure-of-arrays trees resident in HBM.
+//
+// Replaces UTTT::Node / UTTT::pv_mcts_scores (cpp/uttt_mcts.cpp:10-196).  One warp owns one
+// tree (atomics-free per-tree ownership); thousands of trees advance in lock-step "rounds":
+//
+//   tree_round:  [apply]   if the tree has an evaluated leaf waiting: masked + serially
+//                          renormalised priors (:144-163), expansion (:35-44), k sequential
+//                          backups (:47-54)
+//                [select]  descend by PUCT (:57-81) with a warp-level first-max argmax until an
+//                          unexpanded leaf (queue it for the evaluator, fused leaf gather) or a
+//                          terminal node (back up immediately, :115-118, and descend again)
+//                [move]    when the simulation budget is spent: root visit counts -> search
+//                          output, or (self-play) temperature-1 sampling with Philox into the
+//                          history buffers, advance the game, recycle the slot
+//
+// Reference-exact ("compat") semantics.  The reference queues the SAME leaf k = min(batch_size,
+// sims_left) times between flushes because it has no virtual loss; the
+// loop is therefore equivalent to: evaluate the leaf once, append k copies of its child list,
+// back the value up k times sequentially.  That equivalent form is what runs here, and
+// oracle/uttt_oracle.c (which restates the literal queue/flush loop) checks it bit for bit.
+// Children store only (n, w, p, action): positions are recomputed by next_state() during the
+// descent, so a node costs 20 B instead of the reference's ~760 B.
+//
+// All float arithmetic on n/w/p uses explicit round-to-nearest intrinsics in the reference's
+// operation order (no FMA contraction, no reassociation): cpp/setup.py:10 builds with -O3 only.
+#include "common.cuh"
+
+namespace uttt {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int WARPS_PER_BLOCK = 4;
+
+struct TreeView {
+    int32_t* n;
+    float* w;
+    float* p;
+    uint32_t* child;
+    uint32_t* meta;
+    int32_t* path;
+};
+
+__device__ __forceinline__ TreeView view_of(const TreeParams& P, int t) {
+    size_t off = (size_t)t * (size_t)P.node_cap;
+    TreeView v = {P.node_n + off, P.node_w + off, P.node_p + off, P.node_child + off, P.node_meta + off,
+                  P.path + (size_t)t * PATH_CAP};
+    return v;
+}
+
+__device__ __forceinline__ PackedState warp_load_state(const PackedState* p, int lane) {
+    uint32_t x = (lane < 8) ? reinterpret_cast<const uint32_t*>(p)[lane] : 0u;
+    PackedState s;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s.w[i] = __shfl_sync(FULL, x, i);
+    return s;
+}
+__device__ __forceinline__ void warp_store_state(PackedState* p, const PackedState& s, int lane) {
+    uint32_t x = s.w[0];
+#pragma unroll
+    for (int i = 1; i < 8; i++) x = (lane == i) ? s.w[i] : x;
+    if (lane < 8) reinterpret_cast<uint32_t*>(p)[lane] = x;
+}
+
+// cpp/uttt_mcts.cpp:92-103: root expanded up-front with the uniform prior 1/L (never evaluated, Q-M1)
+__device__ void init_root(const TreeParams& P, const TreeView& T, TreeCtl& c, const PackedState& rs, int lane) {
+    uint32_t lm[3];
+    int L = legal_mask(rs, lm);
+    float pu = (L > 0) ? __fdiv_rn(1.0f, (float)L) : 0.0f;
+    if (lane == 0) {
+        T.n[0] = 0; T.w[0] = 0.0f; T.p[0] = 0.0f;
+        T.child[0] = (L > 0) ? 1u : 0u;
+        T.meta[0] = ((uint32_t)L << 8) | 0x7Fu;
+    }
+    for (int a = lane; a < 81; a += 32) {
+        if (legal_bit(lm, a)) {
+            int idx = 1 + legal_rank(lm, a);
+            T.n[idx] = 0; T.w[idx] = 0.0f; T.p[idx] = pu;
+            T.child[idx] = 0u;
+            T.meta[idx] = (uint32_t)a;
+        }
+    }
+    c.n_nodes = 1 + L;
+    c.n_root = L;
+    c.sims_left = P.sims;
+    c.path_len = 0;
+    c.pend_k = 0;
+}
+
+// cpp/uttt_mcts.cpp:47-54, k sequential backups of the same path (values may differ per copy)
+__device__ void backup(const TreeView& T, int plen, int k, const float* vals, int vstride, float v_single, int lane) {
+    __syncwarp();
+    for (int i = lane; i < plen; i += 32) {
+        int node = T.path[i];
+        bool flip = ((plen - 1 - i) & 1) != 0;
+        float w = T.w[node];
+        for (int c = 0; c < k; c++) {
+            float v = vals ? vals[(size_t)c * vstride] : v_single;
+            w = __fadd_rn(w, flip ? -v : v);
+        }
+        T.w[node] = w;
+        T.n[node] += k;
+    }
+    __syncwarp();
+}
+
+// cpp/uttt_mcts.cpp:138-167 for the k queued copies of one leaf
+__device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, int t, int lane) {
+    PackedState st = warp_load_state(P.leaf_state + t, lane);
+    uint32_t lm[3];
+    int L = legal_mask(st, lm);
+    int k = c.pend_k, plen = c.path_len;
+    int leaf = T.path[plen - 1];
+    int base = c.n_nodes;
+    if (base + k * L > P.node_cap) {          // cannot happen with node_cap = 1 + 81 + 81*max_sims
+        if (lane == 0) atomicExch(P.counters + 5, 1ull);
+        c.phase = PHASE_DONE;
+        return;
+    }
+    size_t row = (size_t)c.nn_row * (size_t)P.row_stride;
+    for (int cp = 0; cp < k; cp++) {
+        const float* pol = P.policy + (row + (size_t)cp * P.copy_stride) * 81;
+        // serial fp32 sum over the legal actions in ascending id (:144-152)
+        float sum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint32_t m = lm[j];
+            while (m) {
+                int b = __ffs((int)m) - 1;
+                m &= m - 1u;
+                sum = __fadd_rn(sum, __ldg(pol + 27 * j + b));
+            }
+        }
+        float uni = (L > 0) ? __fdiv_rn(1.0f, (float)L) : 0.0f;
+        int reps = (P.copy_stride == 0) ? k : 1;       // identical rows: write all k copies at once
+        for (int a = lane; a < 81; a += 32) {
+            if (legal_bit(lm, a)) {
+                float pr = (sum > 0.0f) ? __fdiv_rn(__ldg(pol + a), sum) : uni;     // :155-163
+                int r = legal_rank(lm, a);
+                for (int q = 0; q < reps; q++) {
+                    int idx = base + (cp + q) * L + r;
+                    T.n[idx] = 0; T.w[idx] = 0.0f; T.p[idx] = pr;
+                    T.child[idx] = 0u;
+                    T.meta[idx] = (uint32_t)a;
+                }
+            }
+        }
+        if (P.copy_stride == 0) break;
+    }
+    if (lane == 0) {
+        T.child[leaf] = (uint32_t)base;
+        T.meta[leaf] = (T.meta[leaf] & 0xFFu) | ((uint32_t)(k * L) << 8);
+    }
+    c.n_nodes = base + k * L;
+    backup(T, plen, k, P.value + row, P.copy_stride, 0.0f, lane);
+    c.sims_left -= k;
+    c.pend_k = 0;
+    if (lane == 0) atomicAdd(P.counters + 3, (unsigned long long)k);
+}
+
+// Philox temperature-1 sampling over the root visit counts; returns the chosen action.
+__device__ int sample_move(const TreeParams& P, const TreeView& T, const TreeCtl& c, const uint32_t lm[3], int lane) {
+    int L = c.n_root;
+    int tot = 0;
+    for (int i = lane; i < L; i += 32) tot += T.n[1 + i];
+    tot = __reduce_add_sync(FULL, tot);
+    Philox4 r = philox4x32(P.seed, 1u, (uint32_t)c.game, (uint32_t)(c.game >> 32), (uint32_t)c.ply, 0u);
+    uint32_t pick = __umulhi(r.x, (uint32_t)tot);
+    int carry = 0, chosen = -1;
+    for (int base = 0; base < L && chosen < 0; base += 32) {
+        int i = base + lane;
+        int v = (i < L) ? T.n[1 + i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int o = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += o;
+        }
+        incl += carry;
+        unsigned hit = __ballot_sync(FULL, (i < L) && ((uint32_t)incl > pick));
+        if (hit) chosen = base + (__ffs((int)hit) - 1);
+        carry = __shfl_sync(FULL, incl, 31);
+    }
+    if (chosen < 0) chosen = 0;
+    return nth_legal(lm, chosen);
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_begin_kernel(TreeParams P) {
+    int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { P.nn_count[0] = 0; P.nn_count[1] = 0; }
+    if (t >= P.n_trees) return;
+    TreeView T = view_of(P, t);
+    TreeCtl c = P.ctl[t];
+    c.ply = 0; c.game = 0; c.game_idx = -1; c.nn_row = 0; c.pad = 0;
+    PackedState rs;
+    if (P.mode == MODE_SELFPLAY) {
+        unsigned long long g = 0;
+        if (lane == 0) g = atomicAdd(P.counters + 0, 1ull);
+        g = __shfl_sync(FULL, g, 0);
+        if ((int64_t)g >= P.n_games) {
+            c.phase = PHASE_DONE;
+            if (lane == 0) P.ctl[t] = c;
+            return;
+        }
+        c.game = P.game0 + g;
+        c.game_idx = (int32_t)g;
+        init_state(rs);
+        warp_store_state(P.root + t, rs, lane);
+    } else {
+        rs = warp_load_state(P.root + t, lane);
+    }
+    init_root(P, T, c, rs, lane);
+    if (c.n_root == 0) {                     // cpp/uttt_mcts.cpp:96-98: no legal move -> empty result
+        c.phase = PHASE_DONE;
+        if (lane == 0) P.out_n[t] = 0;
+    } else {
+        c.phase = PHASE_SEARCH;
+    }
+    if (lane == 0) P.ctl[t] = c;
+}
+
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreeParams P) {
+    int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    // the other parity's counter was consumed by the previous round's evaluator: reset it
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.nn_count[P.parity ^ 1] = 0;
+    if (t >= P.n_trees) return;
+    TreeCtl c = P.ctl[t];
+    if (c.phase == PHASE_DONE) return;
+    TreeView T = view_of(P, t);
+
+    if (c.phase == PHASE_PENDING) {
+        apply_leaf(P, T, c, t, lane);
+        if (c.phase == PHASE_DONE) { if (lane == 0) P.ctl[t] = c; return; }
+        c.phase = PHASE_SEARCH;
+    }
+
+    PackedState root = warp_load_state(P.root + t, lane);
+    for (;;) {
+        if (c.sims_left <= 0) {
+            // ---------------- the move is decided: root visit counts (cpp/uttt_mcts.cpp:177-180)
+            if (P.mode == MODE_SEARCH) {
+                for (int i = lane; i < c.n_root; i += 32) P.out_counts[(size_t)t * 81 + i] = T.n[1 + i];
+                if (lane == 0) P.out_n[t] = c.n_root;
+                c.phase = PHASE_DONE;
+                break;
+            }
+            uint32_t lm[3];
+            legal_mask(root, lm);
+            size_t hrow = (size_t)c.game_idx * 81 + (size_t)c.ply;
+            warp_store_state(P.hist_states + hrow, root, lane);
+            for (int a = lane; a < 81; a += 32)
+                P.hist_counts[hrow * 81 + a] = legal_bit(lm, a) ? (uint16_t)T.n[1 + legal_rank(lm, a)] : (uint16_t)0;
+            int action = sample_move(P, T, c, lm, lane);
+            if (lane == 0) P.hist_actions[hrow] = (uint8_t)action;
+            PackedState nx;
+            next_state(root, action, nx);
+            root = nx;
+            c.ply += 1;
+            uint32_t lm2[3];
+            int L2 = legal_mask(root, lm2);
+            if (L2 == 0) {                     // game over (lost or drawn): self_play_cpp.py:50-51,95
+                if (lane == 0) {
+                    P.hist_len[c.game_idx] = c.ply;
+                    P.hist_final[c.game_idx] = is_lose(root) ? 1 : 0;
+                    atomicAdd(P.counters + 1, 1ull);
+                    atomicAdd(P.counters + 2, (unsigned long long)c.ply);
+                }
+                unsigned long long g = 0;
+                if (lane == 0) g = atomicAdd(P.counters + 0, 1ull);
+                g = __shfl_sync(FULL, g, 0);
+                if ((int64_t)g >= P.n_games) { c.phase = PHASE_DONE; break; }
+                c.game = P.game0 + g;
+                c.game_idx = (int32_t)g;
+                c.ply = 0;
+                init_state(root);
+            }
+            warp_store_state(P.root + t, root, lane);
+            __syncwarp();
+            init_root(P, T, c, root, lane);
+            __syncwarp();
+        }
+
+        // ---------------- descend (cpp/uttt_mcts.cpp:15-32)
+        PackedState st = root;
+        int node = 0, plen = 1;
+        if (lane == 0) T.path[0] = 0;
+        bool terminal = false, lost = false;
+        uint32_t lm[3];
+        for (;;) {
+            int L = legal_mask(st, lm);
+            lost = is_lose(st);
+            if (lost || L == 0) { terminal = true; break; }
+            uint32_t cbase = T.child[node];
+            if (cbase == 0u) break;                                  // unexpanded leaf
+            int cnt = (int)(T.meta[node] >> 8);
+            // PUCT, cpp/uttt_mcts.cpp:57-81
+            int tot = 0;
+            for (int i = lane; i < cnt; i += 32) tot += T.n[cbase + i];
+            tot = __reduce_add_sync(FULL, tot);
+            float sq = __fsqrt_rn((float)tot);
+            float best = -1e9f;
+            int besti = 0x7FFFFFFF;
+            for (int i = lane; i < cnt; i += 32) {
+                int n = T.n[cbase + i];
+                float w = T.w[cbase + i], p = T.p[cbase + i];
+                float q = (n > 0) ? __fdiv_rn(-w, (float)n) : 0.0f;
+                float u = __fdiv_rn(__fmul_rn(p, sq), (float)(1 + n));
+                float s = __fadd_rn(q, u);
+                if (s > best) { best = s; besti = i; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {                 // first maximum wins (Q-M6)
+                float ob = __shfl_xor_sync(FULL, best, off);
+                int oi = __shfl_xor_sync(FULL, besti, off);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+            }
+            node = (int)cbase + besti;
+            int action = (int)(T.meta[node] & 0xFFu);
+            PackedState nx;
+            next_state(st, action, nx);
+            st = nx;
+            if (lane == 0) T.path[plen] = node;
+            plen++;
+        }
+
+        if (terminal) {
+            // cpp/uttt_mcts.cpp:19-21,115-118: the reference backs up -value with value = -1 for a lost
+            // mover, i.e. +1 lands on the lost node itself (inverted sign, Q-M2); draws back up -0.0f.
+            float v = lost ? 1.0f : -0.0f;
+            if (P.flags & UTTT_SP_CORRECT_TERMINAL_SIGN) v = lost ? -1.0f : 0.0f;
+            backup(T, plen, 1, nullptr, 0, v, lane);
+            c.sims_left -= 1;
+            if (lane == 0) atomicAdd(P.counters + 3, 1ull);
+            continue;
+        }
+
+        // ---------------- queue the leaf for the evaluator; fused leaf gather (cpp/uttt_game.cpp:244-280)
+        int k = min(P.batch, c.sims_left);                            // cpp/uttt_mcts.cpp:127 flush rule
+        int row = 0;
+        if (lane == 0) {
+            row = atomicAdd(P.nn_count + P.parity, 1);
+            atomicAdd(P.counters + 4, 1ull);
+        }
+        row = __shfl_sync(FULL, row, 0);
+        warp_store_state(P.nn_states + row, st, lane);
+        warp_store_state(P.leaf_state + t, st, lane);
+        if (lane == 0) { P.nn_tree[row] = t; P.nn_k[row] = k; }
+        __nv_bfloat16* pl = P.nn_planes + (size_t)row * 243;
+        for (int e = lane; e < 243; e += 32) {
+            int ch = e / 81, cell = e - 81 * ch;
+            int a = action_of_rc(cell / 9, cell % 9);
+            bool v = (ch == 0) ? stone_me(st, a) : (ch == 1 ? stone_opp(st, a) : legal_bit(lm, a));
+            pl[e] = __float2bfloat16(v ? 1.0f : 0.0f);
+        }
+        c.phase = PHASE_PENDING;
+        c.pend_k = k;
+        c.nn_row = row;
+        c.path_len = plen;
+        break;
+    }
+    if (lane == 0) P.ctl[t] = c;
+}
+
+// Deterministic integer-hash evaluator on the device (the "oracle evaluator" of the parity tests):
+// identical arithmetic to orc_hash_eval in oracle/uttt_oracle.c.
+__global__ void __launch_bounds__(128) hash_eval_kernel(const PackedState* __restrict__ states,
+                                                        const int32_t* __restrict__ kk,
+                                                        const int32_t* __restrict__ count, float* __restrict__ policy,
+                                                        float* __restrict__ value, int row_stride, int copy_stride) {
+    int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (row >= *count) return;
+    PackedState st = warp_load_state(states + row, lane);
+    uint32_t h = state_hash(st);
+    int copies = (copy_stride == 0) ? 1 : kk[row];
+    for (int c = 0; c < copies; c++) {
+        size_t r = (size_t)row * row_stride + (size_t)c * copy_stride;
+        for (int a = lane; a < 81; a += 32) {
+            float num = (float)((mix32(h + (uint32_t)a) & 0xFFFFu) + 1u);
+            policy[r * 81 + a] = __fdiv_rn(__fdiv_rn(num, 65536.0f), 81.0f);
+        }
+        if (lane == 0)
+            value[r] = __fdiv_rn(__fsub_rn((float)(int)(mix32(h ^ 0xABCDu) & 0xFFFFu), 32768.0f), 32768.0f);
+    }
+}
+
+// cpp/uttt_mcts.cpp:177-193: counts -> scores (one-hot at the first maximum for T==0, boltzman otherwise)
+__global__ void scores_kernel(const int32_t* __restrict__ counts, const int32_t* __restrict__ nn, int n_trees,
+                              float temperature, float* __restrict__ scores) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trees) return;
+    int n = nn[t];
+    const int32_t* c = counts + (size_t)t * 81;
+    float* s = scores + (size_t)t * 81;
+    if (temperature == 0.0f) {
+        int best = 0;
+        for (int i = 1; i < n; i++)
+            if ((float)c[i] > (float)c[best]) best = i;
+        for (int i = 0; i < n; i++) s[i] = (i == best) ? 1.0f : 0.0f;
+    } else {
+        float inv = __fdiv_rn(1.0f, temperature), sum = 0.0f;
+        for (int i = 0; i < n; i++) {
+            float x = (float)c[i];
+            float v = (inv == 1.0f) ? x : powf(x, inv);     // powf(x, 1) == x exactly
+            s[i] = v;
+            sum = __fadd_rn(sum, v);
+        }
+        if (sum > 0.0f)
+            for (int i = 0; i < n; i++) s[i] = __fdiv_rn(s[i], sum);
+    }
+    for (int i = n; i < 81; i++) s[i] = 0.0f;
+}
+
+// cpp/uttt_mcts.cpp:199-216
+__global__ void boltzman_kernel(const float* __restrict__ xs, int n, float temperature, float* __restrict__ out) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    float inv = __fdiv_rn(1.0f, temperature), sum = 0.0f;
+    for (int i = 0; i < n; i++) {
+        float v = (inv == 1.0f) ? xs[i] : powf(xs[i], inv);
+        out[i] = v;
+        sum = __fadd_rn(sum, v);
+    }
+    if (sum > 0.0f)
+        for (int i = 0; i < n; i++) out[i] = __fdiv_rn(out[i], sum);
+}
+
+cudaError_t launch_tree_begin(const TreeParams& p, cudaStream_t s) {
+    tree_begin_kernel<<<ceil_div(p.n_trees, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_tree_round(const TreeParams& p, cudaStream_t s) {
+    tree_round_kernel<<<ceil_div(p.n_trees, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, s>>>(p);
+    return cudaGetLastError();
+}
+cudaError_t launch_hash_eval(const PackedState* states, const int32_t* k, const int32_t* count, int max_rows,
+                             float* policy, float* value, int row_stride, int copy_stride, cudaStream_t s) {
+    hash_eval_kernel<<<ceil_div(max_rows, 4), 128, 0, s>>>(states, k, count, policy, value, row_stride, copy_stride);
+    return cudaGetLastError();
+}
+cudaError_t launch_scores(const int32_t* counts, const int32_t* n, int n_trees, float temperature, float* scores,
+                          cudaStream_t s) {
+    scores_kernel<<<ceil_div(n_trees, 128), 128, 0, s>>>(counts, n, n_trees, temperature, scores);
+    return cudaGetLastError();
+}
+cudaError_t launch_boltzman(const float* xs, int n, float temperature, float* out, cudaStream_t s) {
+    boltzman_kernel<<<1, 32, 0, s>>>(xs, n, temperature, out);
+    return cudaGetLastError();
+}
+
+}  // namespace uttt

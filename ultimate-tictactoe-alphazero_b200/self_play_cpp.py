@@ -1,0 +1,141 @@
+"""Drop-in replacement for the reference's self_play_cpp.py: `play(model)`, `self_play()` and the
+module constants keep their names, defaults, printed progress line and output format
+(./data/YYYYMMDDHHMMSS.history = pickle of [[x (9,9,3) f32, pi (81,) f64, z int], ...]), but the
+SP_GAME_COUNT games of a cycle run CONCURRENTLY on the GPU inside one C-ABI call
+(uttt_selfplay_run): trees, leaves, network forward, sampling and the history all stay in HBM.
+
+Differences that cannot be avoided: moves are sampled with the engine's counter-based Philox
+stream (seeded from numpy's global RNG, so np.random.seed still makes a run reproducible) instead
+of np.random.choice (self_play_cpp.py:86).  Labelling follows self_play_cpp.py:95-99 verbatim
+unless CORRECTED_LABELS is set.
+"""
+import os
+import pickle
+from datetime import datetime
+
+import numpy as np
+import torch
+
+import engine as _eng
+import uttt_cpp  # noqa: F401  (fails loudly when the CUDA library is missing)
+from dual_network import DualNetwork, device
+
+CPP_AVAILABLE = True
+print("Using B200 CUDA backend for MCTS")
+
+SP_GAME_COUNT = 500       # self_play_cpp.py:26
+SP_TEMPERATURE = 1.0      # self_play_cpp.py:27
+PV_EVALUATE_COUNT = 50    # self_play_cpp.py:30
+MCTS_BATCH_SIZE = 8       # self_play_cpp.py:31
+
+# knobs that do not exist in the reference (defaults reproduce it)
+SP_NUMERICS = "bf16"          # "bf16" (tcgen05 trunk) or "fp32" (CUDA-core parity numerics)
+SP_MAX_SLOTS = 4096           # concurrent games per GPU
+SP_SEED = None                # None: draw from np.random
+CORRECTED_LABELS = False      # True: label from the true winner instead of self_play_cpp.py:95-99
+CORRECTED_TERMINAL_SIGN = False
+
+_engine = None
+last_stats = {}
+
+
+def _get_engine(n_games):
+    global _engine
+    slots = min(max(n_games, 1), SP_MAX_SLOTS)
+    if (_engine is None or _engine.n_slots < slots or _engine.max_games < n_games
+            or _engine.max_sims < PV_EVALUATE_COUNT or _engine.max_batch < MCTS_BATCH_SIZE):
+        if _engine is not None:
+            _engine.close()
+        _engine = _eng.Engine(n_slots=slots, max_sims=PV_EVALUATE_COUNT, max_batch=MCTS_BATCH_SIZE,
+                              max_games=n_games)
+    return _engine
+
+
+def _history_arrays(eng, hist):
+    """packed History -> (xs (N,9,9,3) f32, pis (N,81) f64, zs (N,) int) in game-major order"""
+    st, cn, z = hist.samples()
+    n = st.shape[0]
+    dev = torch.device("cuda", eng.device)
+    st_d = torch.from_numpy(st.view(np.int32)).to(dev)
+    xs = _eng.game_encode(st_d).cpu().numpy()                         # cpp/uttt_game.cpp:244-280 on device
+    legal = xs.reshape(n, 81, 3)[:, :, 2] > 0                          # by picture cell
+    # action id of picture cell (R,C): cpp/uttt_game.cpp:256-257
+    R, Ccol = np.divmod(np.arange(81), 9)
+    act_of_cell = ((R // 3) * 3 + (Ccol // 3)) * 9 + (R % 3) * 3 + (Ccol % 3)
+    legal_by_action = np.zeros((n, 81), bool)
+    legal_by_action[:, act_of_cell] = legal
+    # scores over the legal actions: float32 n/sum (cpp/uttt_mcts.cpp:199-216, T=1) -> float64 renormalised
+    # with numpy's own summation over exactly the legal entries (self_play_cpp.py:74-78), grouped by L
+    tot = cn.sum(axis=1).astype(np.float32)
+    sc32 = cn.astype(np.float32) / tot[:, None]
+    pis = np.zeros((n, 81), np.float64)
+    L = legal_by_action.sum(axis=1)
+    for l in np.unique(L):
+        rows = np.nonzero(L == l)[0]
+        cols = np.nonzero(legal_by_action[rows])[1].reshape(len(rows), l)
+        s64 = np.ascontiguousarray(sc32[rows[:, None], cols].astype(np.float64))
+        s64 = s64 / np.sum(s64, axis=1)[:, None]
+        pis[rows[:, None], cols] = s64
+    if CORRECTED_LABELS:
+        z = _corrected_labels(hist)
+    return xs, pis, z.astype(np.int64)
+
+
+def _corrected_labels(hist):
+    """value from each mover's own perspective (the labelling of the reference's self_play.py:21-25,96)"""
+    lens = hist.lens.astype(np.int64)
+    mask = np.arange(81)[None, :] < lens[:, None]
+    # the final position's mover lost iff final != 0; ply t has the same mover as the final position
+    # iff (len - t) is even
+    par = ((lens[:, None] - np.arange(81)[None, :]) % 2) == 0
+    zf = np.where(hist.final != 0, -1, 0)[:, None]
+    return np.where(par, zf, -zf)[mask].astype(np.int8)
+
+
+def _to_reference_format(xs, pis, zs):
+    return [[xs[i], pis[i], int(zs[i])] for i in range(len(zs))]
+
+
+def _run(model, n_games):
+    eng = _get_engine(n_games)
+    model.eval()
+    eng.upload_model(model)
+    seed = int(np.random.randint(0, 2 ** 31 - 1)) if SP_SEED is None else int(SP_SEED)
+    ev = _eng.EVAL_NET_FP32 if SP_NUMERICS == "fp32" else _eng.EVAL_NET_BF16
+    flags = _eng.SP_CORRECT_TERMINAL_SIGN if CORRECTED_TERMINAL_SIGN else 0
+    if SP_TEMPERATURE != 1.0:
+        raise NotImplementedError("the on-device sampler implements SP_TEMPERATURE == 1.0 (the reference's setting)")
+    hist = eng.selfplay(n_games, sims=PV_EVALUATE_COUNT, batch=MCTS_BATCH_SIZE, seed=seed, evaluator=ev, flags=flags)
+    last_stats.update(plies=int(hist.stats[0]), sims=int(hist.stats[1]), evals=int(hist.stats[2]),
+                      rounds=int(hist.stats[3]), seed=seed)
+    return eng, hist
+
+
+def play(model, use_cpp=True):
+    """self_play_cpp.py:34-101: one game -> [[x, pi, z], ...]"""
+    eng, hist = _run(model, 1)
+    return _to_reference_format(*_history_arrays(eng, hist))
+
+
+def self_play(use_cpp=True):
+    """self_play_cpp.py:104-130: SP_GAME_COUNT games -> ./data/<timestamp>.history"""
+    model = DualNetwork().to(device)
+    model.load_state_dict(torch.load("./model/best.pth", map_location=device, weights_only=True))
+    model.eval()
+    eng, hist = _run(model, SP_GAME_COUNT)
+    history = _to_reference_format(*_history_arrays(eng, hist))
+    print(f"\rSelfPlay {SP_GAME_COUNT}/{SP_GAME_COUNT} (Backend: C++)", end="")
+    print("")
+    now = datetime.now()
+    file_name = "./data/{:04}{:02}{:02}{:02}{:02}{:02}.history".format(
+        now.year, now.month, now.day, now.hour, now.minute, now.second)
+    os.makedirs("./data", exist_ok=True)
+    with open(file_name, mode="wb") as f:
+        pickle.dump(history, f)
+    return file_name
+
+
+if __name__ == "__main__":
+    from pv_mcts_cpp import check_cpp_compatibility
+    check_cpp_compatibility()
+    self_play()
