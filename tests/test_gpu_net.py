@@ -40,7 +40,7 @@ def _damped(model):
         for blk in model.residual_blocks:
             blk.bn2.weight.mul_(0.3)
         model.policy_fc.weight.mul_(0.05)
-        model.value_fc1.weight.mul_(0.2)
+        model.value_fc1.weight.mul_(0.1)
         model.value_fc2.weight.mul_(0.2)
         # non-trivial BN statistics so that folding is exercised
         g = torch.Generator().manual_seed(5)
