@@ -173,6 +173,10 @@ int uttt_selfplay_fetch(uttt_engine *e, int64_t n_games, uint32_t *hist_states, 
  * launching stream and launch counts; kind: 0 tree kernels, 1 trunk, 2 heads, 3 everything */
 int uttt_last_run_profile(uttt_engine *e, int kind, double *ms_out, int64_t *launches_out);
 
+/* diagnostics: clock64 timeline of CTA 0 of the last tensor-core trunk launch, [32 layers][4]:
+ * MMA start, MMA issue done, accumulators ready (epilogue start), epilogue done */
+int uttt_debug_trunk_timeline(uttt_engine *e, int64_t *out128);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,8 +42,9 @@ struct uttt_engine {
     float* scores;          // [n_slots][81]
     float* act_a;           // [n_slots][81][128] fp32
     float* act_b;
-    float* tc_resid;        // [groups][512][128] fp32 residual stream of the tensor-core trunk
+    float* tc_resid;        // [n_sm][32][512][4] fp32 residual stream of the tensor-core trunk (per CTA)
     int32_t* fwd_count;     // device int for uttt_net_forward
+    long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0 (diagnostics)
     NetWeights w;
     unsigned long long* h_counters;   // pinned [8]
     int32_t* h_count;                 // pinned [2]
@@ -75,14 +76,17 @@ int run_evaluator(uttt_engine* e, int evaluator, const int32_t* count, int max_r
         return 0;
     }
     UTTT_CHECK(e->w.loaded, "network weights not uploaded (uttt_upload_weights)");
-    if (ev3) cudaEventRecord(ev3[0], s);
     if (evaluator == UTTT_EVAL_NET_FP32) {
+        if (ev3) cudaEventRecord(ev3[0], s);
         UTTT_CUDA_OK(launch_trunk_fp32(e->w, e->tp.nn_planes, count, max_rows, e->act_a, e->act_b, s));
         e->prof_launches[1] += 1 + 2 * NET_BLOCKS;
     } else if (evaluator == UTTT_EVAL_NET_BF16) {
+        // conv_input is accounted to the tree/gather share; the trunk events bracket trunk_tc_kernel alone
         UTTT_CUDA_OK(launch_conv_input(e->w, e->tp.nn_planes, count, max_rows, e->act_a, s));
-        UTTT_CUDA_OK(launch_trunk_tc(e->w, e->act_a, count, max_rows, e->tc_resid, e->n_sm, s));
-        e->prof_launches[1] += 2;
+        e->prof_launches[0] += 1;
+        if (ev3) cudaEventRecord(ev3[0], s);
+        UTTT_CUDA_OK(launch_trunk_tc(e->w, e->act_a, count, max_rows, e->tc_resid, e->n_sm, s, e->tc_dbg));
+        e->prof_launches[1] += 1;
     } else {
         UTTT_CHECK(false, "evaluator %d cannot run on the device", evaluator);
     }
@@ -134,7 +138,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
         ealloc(e, &e->act_a, S * 81 * 128) || ealloc(e, &e->act_b, S * 81 * 128) ||
-        ealloc(e, &e->tc_resid, ((S + 4) / 5) * 512 * 128) || ealloc(e, &e->fwd_count, 1)) {
+        ealloc(e, &e->tc_resid, (size_t)e->n_sm * 512 * 128) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128)) {
         uttt_destroy(e);
         return 1;
     }
@@ -473,6 +477,14 @@ int uttt_selfplay_run(uttt_engine* e, int64_t n_games, uint64_t game0, int32_t s
                       uint8_t* hist_actions, int32_t* hist_len, int8_t* hist_final, int64_t* stats) {
     if (uttt_selfplay_run_device(e, n_games, game0, sims, batch, seed, evaluator, flags, stats, nullptr)) return 1;
     return uttt_selfplay_fetch(e, n_games, hist_states, hist_counts, hist_actions, hist_len, hist_final);
+}
+
+int uttt_debug_trunk_timeline(uttt_engine* e, int64_t* out128) {
+    UTTT_CHECK(e && out128, "null argument");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    UTTT_CUDA_OK(cudaDeviceSynchronize());
+    UTTT_CUDA_OK(cudaMemcpy(out128, e->tc_dbg, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 int uttt_last_run_profile(uttt_engine* e, int kind, double* ms_out, int64_t* launches_out) {

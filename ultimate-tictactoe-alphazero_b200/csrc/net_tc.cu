@@ -22,7 +22,9 @@
 //     and re-read by the same thread; only conv_input's output and the last block's output touch
 //     HBM otherwise.
 //
-// Warp roles: warps 0-15 epilogue, warp 16 weight producer, warp 17 MMA issuer + TMEM owner.
+// Warp roles: warps 0-15 epilogue, warp 16 weight producer, warps 17-20 MMA issuers (one elected lane each,
+// one accumulator tile each: a single issuing thread cannot keep the tensor pipe busy with K=16 MMAs of
+// 64 cycles because every issue costs ~80 cycles of descriptor/uniform-register traffic); warp 17 owns TMEM.
 #include "common.cuh"
 
 namespace uttt {
@@ -40,7 +42,8 @@ constexpr int TC_STAGES = 5;
 constexpr int TC_STAGES_PER_LAYER = 18;
 constexpr int TC_BAR_OFF = TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES;
 constexpr int TC_SMEM_BYTES = TC_BAR_OFF + 256;
-constexpr int TC_THREADS = 18 * 32;
+constexpr int TC_ISSUERS = 4;                  // one MMA-issuing warp per accumulator tile
+constexpr int TC_THREADS = (17 + TC_ISSUERS) * 32;
 constexpr int TC_EPI_WARPS = 16;
 
 // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A and B, N=128, M=128
@@ -64,7 +67,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // bounded wait: a protocol bug must trap instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0) {
     uint32_t ok = 0;
     long long t0 = 0;
     for (uint32_t it = 0;; it++) {
@@ -76,6 +79,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             : "r"(bar), "r"(parity)
             : "memory");
         if (ok) return;
+        if (backoff_ns) __nanosleep(backoff_ns);     // keep pollers off the shared-memory port the MMA reads through
         if ((it & 1023u) == 1023u) {
             long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -121,7 +125,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -133,27 +143,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
                 const float* __restrict__ bias,         // [32][128]
                 float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
-                float* resid,                           // [groups][512][128] fp32 skip connection
-                const int32_t* __restrict__ count) {
+                float* resid,                           // [gridDim][32 col groups][512 rows][4] fp32 skip connection
+                const int32_t* __restrict__ count,
+                long long* dbg) {                       // optional [32][4] clock64 timeline of CTA 0 (diagnostics)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pos = *count;
-    const int n_groups = (n_pos + TC_P - 1) / TC_P;
+    // positions per group: as few as keeps every group in the first wave (latency matters when the batch is
+    // small), at most 5; 4 positions would need the same 4 tiles as 5, so it is never chosen.
+    int P = (n_pos + (int)gridDim.x - 1) / (int)gridDim.x;
+    P = P < 1 ? 1 : (P >= 4 ? TC_P : P);
+    const int tiles = (P * TC_POS_ROWS + 127) / 128;
+    const int n_groups = (n_pos + P - 1) / P;
     if ((int)blockIdx.x >= n_groups) return;
 
     uint8_t* sA = smem;
     const uint32_t sA_u = smem_u32(sA);
     const uint32_t sB_u = sA_u + TC_A_BYTES;
     const uint32_t bar_u = sA_u + TC_BAR_OFF;
-    // barriers: full[5] @0, empty[5] @40, accum_full @80, act_ready @88; tmem base holder @96
+    // barriers: full[5] @0, empty[5] @40, accum_full[4] @80, act_ready[4] @112; tmem base holder @144
+    // Per-tile barriers let the four accumulator tiles drift apart: while one tile is in its epilogue the
+    // other tiles' MMAs keep the tensor pipe busy.  A tile only synchronises with its row neighbours, because
+    // its MMAs read 11 halo rows of the tile before and after it:
+    //   act_ready[t]  <- epilogue warps (t,0..3), (t-1,3), (t+1,0)      (the rows tile t's MMAs read are written)
+    //   accum_full[t] <- issuer t's tcgen05.commit                        (tile t's MMAs of this layer retired)
+    //   epilogue warp (t,q) may overwrite its rows once accum_full[t], and accum_full[t-1] (q==0) or
+    //   accum_full[t+1] (q==3), have completed: nobody reads the old values any more.
     const uint32_t bar_full = bar_u, bar_empty = bar_u + 8 * TC_STAGES, bar_accum = bar_u + 16 * TC_STAGES,
-                   bar_act = bar_u + 16 * TC_STAGES + 8;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + TC_BAR_OFF + 16 * TC_STAGES + 16);
+                   bar_act = bar_u + 16 * TC_STAGES + 32;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + TC_BAR_OFF + 16 * TC_STAGES + 64);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_STAGES; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-        mbar_init(bar_accum, 1);
-        mbar_init(bar_act, TC_EPI_WARPS);
+        for (int i = 0; i < TC_STAGES; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, tiles); }
+        for (int t = 0; t < TC_TILES; t++) {
+            mbar_init(bar_accum + 8 * t, 1);
+            mbar_init(bar_act + 8 * t, 4 + (t > 0 ? 1 : 0) + (t < tiles - 1 ? 1 : 0));
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 17) {
@@ -175,13 +200,14 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
         if (warp < TC_EPI_WARPS) {
             // ================= epilogue warps: one GEMM row (TMEM lane) per thread =================
             const int tile = warp >> 2, quarter = warp & 3;
+            if (tile >= tiles) continue;
             const int m = tile * 128 + quarter * 32 + lane;
             const int pos = m / TC_POS_ROWS, idx = m - pos * TC_POS_ROWS;
             const int r = idx / 10, c = idx - 10 * r;
-            const int gpos = g * TC_P + pos;
-            const bool valid = (pos < TC_P) && (r < 9) && (c < 9) && (gpos < n_pos);
+            const int gpos = g * P + pos;
+            const bool valid = (pos < P) && (r < 9) && (c < 9) && (gpos < n_pos);
             float* arow = act + ((size_t)gpos * 81 + (size_t)(r * 9 + c)) * 128;
-            float* rrow = resid + ((size_t)g * TC_M + (size_t)m) * 128;
+            float4* rrow = reinterpret_cast<float4*>(resid) + (size_t)blockIdx.x * (32 * TC_M) + (size_t)m;
             uint8_t* srow = sA + (size_t)(TC_LEAD + m) * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile * 128);
 
@@ -193,7 +219,7 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 for (int j = 0; j < 8; j++) {
                     float4 x = valid ? reinterpret_cast<const float4*>(arow + ch * 32)[j] : make_float4(0, 0, 0, 0);
                     v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-                    if (valid) reinterpret_cast<float4*>(rrow + ch * 32)[j] = x;
+                    if (valid) rrow[(size_t)(ch * 8 + j) * TC_M] = x;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -202,13 +228,23 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                     *reinterpret_cast<uint4*>(srow + (size_t)(ch * 4 + j) * TC_PANEL_BYTES) = pk;
                 }
             }
+            const bool nb_lo = (quarter == 0) && (tile > 0);            // rows also read by tile-1's MMAs
+            const bool nb_hi = (quarter == 3) && (tile < tiles - 1);    // rows also read by tile+1's MMAs
             fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_act);
+            if (lane == 0) {
+                mbar_arrive(bar_act + 8 * tile);
+                if (nb_lo) mbar_arrive(bar_act + 8 * (tile - 1));
+                if (nb_hi) mbar_arrive(bar_act + 8 * (tile + 1));
+            }
 
 #pragma unroll 1
             for (int layer = 0; layer < NET_LAYERS; layer++) {
-                mbar_wait(bar_accum, (uint32_t)((iter * NET_LAYERS + layer) & 1));
+                const uint32_t lpar = (uint32_t)((iter * NET_LAYERS + layer) & 1);
+                mbar_wait(bar_accum + 8 * tile, lpar, 128);
+                if (nb_lo) mbar_wait(bar_accum + 8 * (tile - 1), lpar, 64);
+                if (nb_hi) mbar_wait(bar_accum + 8 * (tile + 1), lpar, 64);
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
                 const bool second = (layer & 1) != 0;          // conv2 of a block: add the skip connection
                 const bool last = (layer == NET_LAYERS - 1);
@@ -217,25 +253,37 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 for (int ch = 0; ch < 4; ch++) {
                     float v[32];
                     tmem_ld32(taddr + (uint32_t)(ch * 32), v);
+                    float4 x[8];
+                    if (second && valid) {                       // skip-connection loads overlap the TMEM load
+#pragma unroll
+                        for (int j = 0; j < 8; j++) x[j] = rrow[(size_t)(ch * 8 + j) * TC_M];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) x[j] = make_float4(0, 0, 0, 0);
+                    }
+                    tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 32) + j);
-                        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                        v[4 * j] = fmaxf(v[4 * j] + b4.x + x[j].x, 0.0f);
+                        v[4 * j + 1] = fmaxf(v[4 * j + 1] + b4.y + x[j].y, 0.0f);
+                        v[4 * j + 2] = fmaxf(v[4 * j + 2] + b4.z + x[j].z, 0.0f);
+                        v[4 * j + 3] = fmaxf(v[4 * j + 3] + b4.w + x[j].w, 0.0f);
+                    }
+                    if (!valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) v[j] = 0.0f;
                     }
                     if (second && valid) {
+                        if (last) {
 #pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            float4 x = reinterpret_cast<const float4*>(rrow + ch * 32)[j];
-                            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+                            for (int j = 0; j < 8; j++)
+                                reinterpret_cast<float4*>(arow + ch * 32)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; j++)
+                                rrow[(size_t)(ch * 8 + j) * TC_M] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j++) v[j] = valid ? fmaxf(v[j], 0.0f) : 0.0f;
-                    if (second && valid) {
-                        float* dst = last ? arow : rrow;
-#pragma unroll
-                        for (int j = 0; j < 8; j++)
-                            reinterpret_cast<float4*>(dst + ch * 32)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                     if (!last) {
 #pragma unroll
@@ -250,8 +298,13 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_act);
+                    if (lane == 0) {
+                        mbar_arrive(bar_act + 8 * tile);
+                        if (nb_lo) mbar_arrive(bar_act + 8 * (tile - 1));
+                        if (nb_hi) mbar_arrive(bar_act + 8 * (tile + 1));
+                    }
                 }
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 3] = clock64();
             }
             tc_fence_before();
         } else if (warp == 16) {
@@ -270,11 +323,17 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 __syncwarp();
             }
         } else {
-            // ================= MMA issuer (one elected lane) =================
+            // ================= MMA issuers: warp 17+t drives accumulator tile t =================
+            const int tile = warp - 17;
+            if (tile >= tiles) continue;
+            const bool leader = elect_one();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(tile * 128);
+            const uint32_t a_tile = sA_u + (uint32_t)(TC_LEAD + tile * 128) * 16u;
 #pragma unroll 1
             for (int layer = 0; layer < NET_LAYERS; layer++) {
-                mbar_wait(bar_act, (uint32_t)((iter * NET_LAYERS + layer) & 1));
+                mbar_wait(bar_act + 8 * tile, (uint32_t)((iter * NET_LAYERS + layer) & 1), 32);
                 tc_fence_after();
+                if (dbg && blockIdx.x == 0 && iter == 0 && tile == 0 && leader) dbg[layer * 4 + 0] = clock64();
 #pragma unroll 1
                 for (int s = 0; s < TC_STAGES_PER_LAYER; s++) {
                     const int gn = (iter * NET_LAYERS + layer) * TC_STAGES_PER_LAYER + s;
@@ -282,23 +341,21 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                     const uint32_t par = (uint32_t)((gn / TC_STAGES) & 1);
                     mbar_wait(bar_full + 8 * stage, par);
                     tc_fence_after();
-                    if (lane == 0) {
+                    if (leader) {
                         const int tap = s >> 1, half = s & 1;
                         const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                        const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * TC_PANEL_BYTES;
+                        const uint32_t b0 = sB_u + (uint32_t)stage * TC_STAGE_BYTES;
 #pragma unroll
-                        for (int tile = 0; tile < TC_TILES; tile++) {
-#pragma unroll
-                            for (int ks = 0; ks < 4; ks++) {
-                                const int kg = half * 4 + ks;
-                                const uint32_t a_addr = sA_u + (uint32_t)(2 * kg) * TC_PANEL_BYTES +
-                                                        (uint32_t)(TC_LEAD + tile * 128 + shift) * 16u;
-                                const uint32_t b_addr = sB_u + (uint32_t)stage * TC_STAGE_BYTES + (uint32_t)ks * 4096u;
-                                umma_bf16(tmem_base + (uint32_t)(tile * 128), make_desc(a_addr, TC_PANEL_BYTES, 128),
-                                          make_desc(b_addr, 2048, 128), TC_IDESC, (uint32_t)((s | ks) != 0));
-                            }
+                        for (int ks = 0; ks < 4; ks++) {
+                            umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * TC_PANEL_BYTES, TC_PANEL_BYTES, 128),
+                                      make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), TC_IDESC, (uint32_t)((s | ks) != 0));
                         }
                         umma_commit(bar_empty + 8 * stage);          // frees the weight stage when the MMAs retire
-                        if (s == TC_STAGES_PER_LAYER - 1) umma_commit(bar_accum);   // accumulators complete
+                        if (s == TC_STAGES_PER_LAYER - 1) {
+                            umma_commit(bar_accum + 8 * tile);       // this tile's accumulator is complete
+                            if (dbg && blockIdx.x == 0 && iter == 0 && tile == 0) dbg[layer * 4 + 1] = clock64();
+                        }
                     }
                     __syncwarp();
                 }
@@ -320,11 +377,10 @@ cudaError_t trunk_tc_init() {
 }
 
 cudaError_t launch_trunk_tc(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* resid,
-                            int n_sm, cudaStream_t s) {
-    int max_groups = (max_rows + TC_P - 1) / TC_P;
-    int grid = max_groups < n_sm ? max_groups : n_sm;
+                            int n_sm, cudaStream_t s, long long* dbg) {
+    int grid = max_rows < n_sm ? max_rows : n_sm;
     if (grid < 1) grid = 1;
-    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.res_b, act, resid, count);
+    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.res_b, act, resid, count, dbg);
     return cudaGetLastError();
 }
 

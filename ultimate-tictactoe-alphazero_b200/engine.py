@@ -67,6 +67,7 @@ ABI = {
     "uttt_selfplay_run_device": ([_vp, C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_uint32, C.c_int32,
                                   C.c_int32, _vp, _vp], C.c_int),
     "uttt_selfplay_fetch": ([_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "uttt_debug_trunk_timeline": ([_vp, _vp], C.c_int),
     "uttt_last_run_profile": ([_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
 }
 
@@ -346,6 +347,13 @@ class Engine:
         _check(self.lib.uttt_selfplay_fetch(self.h, n_games, _ptr(hist.states), _ptr(hist.counts), _ptr(hist.actions),
                                             _ptr(hist.lens), _ptr(hist.final)))
         return hist
+
+    def trunk_timeline(self):
+        """clock64 stamps of CTA 0 of the last tcgen05 trunk launch: (32,4) = MMA start, MMA issued,
+        accumulators ready, epilogue done"""
+        out = np.zeros(128, np.int64)
+        _check(self.lib.uttt_debug_trunk_timeline(self.h, _ptr(out)))
+        return out.reshape(32, 4)
 
     def last_run_profile(self):
         """-> {kind: (ms, launches)} for tree / trunk / heads / all kernels of the last self-play run"""
