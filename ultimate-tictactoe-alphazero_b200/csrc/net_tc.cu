@@ -18,13 +18,15 @@
 //   * D accumulators: 4 x (128 lanes x 128 fp32 columns) = all 512 TMEM columns.
 //   * Epilogue (16 warps, one TMEM lane quarter of one tile each): tcgen05.ld -> +shift (+skip)
 //     -> ReLU -> zero the padding rows -> bf16 -> back into the SAME shared-memory buffer in place
-//     (all MMAs of the layer have completed).  The fp32 skip connection lives in HBM/L2, written
+//     (all MMAs of the layer have completed).  The skip connection (fp16 panels) lives in HBM/L2, written
 //     and re-read by the same thread; only conv_input's output and the last block's output touch
 //     HBM otherwise.
 //
 // Warp roles: warps 0-15 epilogue, warp 16 weight producer, warps 17-20 MMA issuers (one elected lane each,
 // one accumulator tile each: a single issuing thread cannot keep the tensor pipe busy with K=16 MMAs of
 // 64 cycles because every issue costs ~80 cycles of descriptor/uniform-register traffic); warp 17 owns TMEM.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace uttt {
@@ -126,6 +128,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// the skip connection is kept as fp16 (post-ReLU activations of a BatchNorm net are far inside the fp16
+// range, clamped anyway): 2 bytes per value like bf16 but 3 more mantissa bits, so the skip path does not add
+// a second bf16 rounding per block on top of the bf16 MMA operands.
+__device__ __forceinline__ void f16x8_add(const uint4& q, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 f = __half22float2(h[i]);
+        v[2 * i] += f.x;
+        v[2 * i + 1] += f.y;
+    }
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(fminf(lo, 65504.0f), fminf(hi, 65504.0f));
+    return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ bool elect_one() {
@@ -143,7 +171,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
                 const float* __restrict__ bias,         // [32][128]
                 float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
-                float* resid,                           // [gridDim][32 col groups][512 rows][4] fp32 skip connection
+                float* resid,                           // [gridDim][16 panels][512 rows][8] fp16 skip connection (L2-resident)
                 const int32_t* __restrict__ count,
                 long long* dbg) {                       // optional [32][4] clock64 timeline of CTA 0 (diagnostics)
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -207,7 +235,7 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
             const int gpos = g * P + pos;
             const bool valid = (pos < P) && (r < 9) && (c < 9) && (gpos < n_pos);
             float* arow = act + ((size_t)gpos * 81 + (size_t)(r * 9 + c)) * 128;
-            float4* rrow = reinterpret_cast<float4*>(resid) + (size_t)blockIdx.x * (32 * TC_M) + (size_t)m;
+            uint4* rrow = reinterpret_cast<uint4*>(resid) + (size_t)blockIdx.x * (16 * TC_M) + (size_t)m;
             uint8_t* srow = sA + (size_t)(TC_LEAD + m) * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile * 128);
 
@@ -219,13 +247,16 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 for (int j = 0; j < 8; j++) {
                     float4 x = valid ? reinterpret_cast<const float4*>(arow + ch * 32)[j] : make_float4(0, 0, 0, 0);
                     v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
-                    if (valid) rrow[(size_t)(ch * 8 + j) * TC_M] = x;
                 }
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
                     *reinterpret_cast<uint4*>(srow + (size_t)(ch * 4 + j) * TC_PANEL_BYTES) = pk;
+                    if (valid)
+                        rrow[(size_t)(ch * 4 + j) * TC_M] =
+                            make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+                                       pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
                 }
             }
             const bool nb_lo = (quarter == 0) && (tile > 0);            // rows also read by tile-1's MMAs
@@ -249,48 +280,44 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 const bool second = (layer & 1) != 0;          // conv2 of a block: add the skip connection
                 const bool last = (layer == NET_LAYERS - 1);
                 const float* bl = bias + layer * 128;
-#pragma unroll 1
-                for (int ch = 0; ch < 4; ch++) {
-                    float v[32];
-                    tmem_ld32(taddr + (uint32_t)(ch * 32), v);
-                    float4 x[8];
-                    if (second && valid) {                       // skip-connection loads overlap the TMEM load
+                // 8 chunks of 16 accumulator columns, TMEM loads double-buffered against the math / stores
+                float va[16], vb[16];
+                tmem_ld16(taddr, va);
 #pragma unroll
-                        for (int j = 0; j < 8; j++) x[j] = rrow[(size_t)(ch * 8 + j) * TC_M];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; j++) x[j] = make_float4(0, 0, 0, 0);
+                for (int ch = 0; ch < 8; ch++) {
+                    float* v = (ch & 1) ? vb : va;
+                    uint4 rx0 = make_uint4(0, 0, 0, 0), rx1 = make_uint4(0, 0, 0, 0);
+                    if (second && valid) {                       // skip connection (fp16 panels in L2)
+                        rx0 = rrow[(size_t)(2 * ch) * TC_M];
+                        rx1 = rrow[(size_t)(2 * ch + 1) * TC_M];
                     }
                     tmem_ld_wait();
+                    if (ch < 7) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 32) + j);
-                        v[4 * j] = fmaxf(v[4 * j] + b4.x + x[j].x, 0.0f);
-                        v[4 * j + 1] = fmaxf(v[4 * j + 1] + b4.y + x[j].y, 0.0f);
-                        v[4 * j + 2] = fmaxf(v[4 * j + 2] + b4.z + x[j].z, 0.0f);
-                        v[4 * j + 3] = fmaxf(v[4 * j + 3] + b4.w + x[j].w, 0.0f);
+                    for (int j = 0; j < 4; j++) {
+                        float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 16) + j);
+                        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
                     }
-                    if (!valid) {
+                    f16x8_add(rx0, v);
+                    f16x8_add(rx1, v + 8);
 #pragma unroll
-                        for (int j = 0; j < 32; j++) v[j] = 0.0f;
-                    }
-                    if (second && valid) {
-                        if (last) {
+                    for (int j = 0; j < 16; j++) v[j] = valid ? fmaxf(v[j], 0.0f) : 0.0f;
+                    if (last) {
+                        if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                reinterpret_cast<float4*>(arow + ch * 32)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 8; j++)
-                                rrow[(size_t)(ch * 8 + j) * TC_M] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < 4; j++)
+                                reinterpret_cast<float4*>(arow + ch * 16)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                         }
-                    }
-                    if (!last) {
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
+                        for (int j = 0; j < 2; j++) {
                             uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
                                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-                            *reinterpret_cast<uint4*>(srow + (size_t)(ch * 4 + j) * TC_PANEL_BYTES) = pk;
+                            *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * TC_PANEL_BYTES) = pk;
+                            if (second && valid)
+                                rrow[(size_t)(ch * 2 + j) * TC_M] =
+                                    make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
+                                               pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
                         }
                     }
                 }
