@@ -110,9 +110,12 @@ def test_selfplay_hash_matches_reference_goldens(eng, golden_dir):
         off += n
 
 
-def test_selfplay_many_games_with_slot_recycling_vs_oracle():
+@pytest.mark.parametrize("slots", [48, 160])      # 160 slots: two overlapped lanes on two streams
+def test_selfplay_many_games_with_slot_recycling_vs_oracle(slots):
     import engine
-    e = engine.Engine(n_slots=48, max_sims=50, max_batch=8, max_games=200)
+    os.environ["UTTT_LANE_THRESHOLD"] = "100"
+    e = engine.Engine(n_slots=slots, max_sims=50, max_batch=8, max_games=200)
+    del os.environ["UTTT_LANE_THRESHOLD"]
     try:
         h = e.selfplay(200, sims=50, batch=8, seed=9, evaluator=engine.EVAL_HASH, game0=1000)
         assert (h.lens > 0).all() and h.stats[0] == h.lens.sum()

@@ -64,12 +64,8 @@ struct TreeParams {
     PackedState* leaf_state;  // [n_trees]
     TreeCtl* ctl;             // [n_trees]
     int32_t* path;            // [n_trees][PATH_CAP]
-    // node SoA, [n_trees][node_cap]
-    int32_t* node_n;
-    float* node_w;
-    float* node_p;
-    uint32_t* node_child;     // index of first child, 0 = unexpanded
-    uint32_t* node_meta;      // (n_children << 8) | action
+    // nodes, [n_trees][node_cap], 16 B each: {n:16 | action<<16, w, p, first_child:20 | n_children<<20}
+    uint4* nodes;
     // evaluator queue (rows are compacted with an atomic counter, double-buffered by round parity)
     PackedState* nn_states;   // [rows]
     __nv_bfloat16* nn_planes; // [rows][3*81]

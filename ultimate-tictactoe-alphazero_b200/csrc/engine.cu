@@ -11,6 +11,7 @@
 // enqueued back to back on one stream with no host synchronisation except a progress check
 // every CHECK_EVERY rounds.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -22,7 +23,8 @@ using namespace uttt;
 namespace {
 
 constexpr int CHECK_EVERY = 16;
-constexpr int EV_POOL = CHECK_EVERY * 4;
+constexpr int N_LANES = 2;
+constexpr int EV_POOL = CHECK_EVERY * 4 * N_LANES;
 
 __global__ void set_int_kernel(int32_t* p, int32_t v) { *p = v; }
 
@@ -36,6 +38,8 @@ struct uttt_engine {
     int n_sm;
     int node_cap;
     cudaStream_t stream;
+    cudaStream_t lane_stream[N_LANES];
+    cudaEvent_t ev_fork, ev_join[N_LANES];
     TreeParams tp;          // device pointers (n_trees / mode / sims set per call)
     float* policy;          // [n_slots*max_batch][81]
     float* value;           // [n_slots*max_batch]
@@ -45,6 +49,7 @@ struct uttt_engine {
     float* tc_resid;        // [n_sm][32][512][4] fp32 residual stream of the tensor-core trunk (per CTA)
     int32_t* fwd_count;     // device int for uttt_net_forward
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0 (diagnostics)
+    int lane_threshold;     // slots from which self-play splits into two overlapped lanes
     NetWeights w;
     unsigned long long* h_counters;   // pinned [8]
     int32_t* h_count;                 // pinned [2]
@@ -66,11 +71,32 @@ int ealloc(uttt_engine* e, T** p, size_t n) {
     return 0;
 }
 
-int run_evaluator(uttt_engine* e, int evaluator, const int32_t* count, int max_rows, cudaStream_t s,
+// the buffers one evaluator invocation works on (the whole engine, or one lane's slice of it)
+struct EvalBufs {
+    const PackedState* nn_states;
+    const int32_t* nn_k;
+    const __nv_bfloat16* nn_planes;
+    float *policy, *value, *act_a, *act_b, *resid;
+};
+
+EvalBufs bufs_of(uttt_engine* e, size_t first_slot, int lane) {
+    EvalBufs b;
+    b.nn_states = e->tp.nn_states + first_slot;
+    b.nn_k = e->tp.nn_k + first_slot;
+    b.nn_planes = e->tp.nn_planes + first_slot * 243;
+    b.policy = e->policy + first_slot * e->cfg.max_batch * 81;
+    b.value = e->value + first_slot * e->cfg.max_batch;
+    b.act_a = e->act_a + first_slot * 81 * 128;
+    b.act_b = e->act_b + first_slot * 81 * 128;
+    b.resid = e->tc_resid + (size_t)lane * e->n_sm * 512 * 64;     // fp16 panels: 128 KiB per CTA
+    return b;
+}
+
+int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_t* count, int max_rows, cudaStream_t s,
                   cudaEvent_t* ev3 /* optional: [0] before trunk, [1] after trunk, [2] after heads */) {
     if (evaluator == UTTT_EVAL_HASH) {
         if (ev3) cudaEventRecord(ev3[0], s);
-        UTTT_CUDA_OK(launch_hash_eval(e->tp.nn_states, e->tp.nn_k, count, max_rows, e->policy, e->value, 1, 0, s));
+        UTTT_CUDA_OK(launch_hash_eval(b.nn_states, b.nn_k, count, max_rows, b.policy, b.value, 1, 0, s));
         if (ev3) { cudaEventRecord(ev3[1], s); cudaEventRecord(ev3[2], s); }
         e->prof_launches[1] += 1;
         return 0;
@@ -78,20 +104,20 @@ int run_evaluator(uttt_engine* e, int evaluator, const int32_t* count, int max_r
     UTTT_CHECK(e->w.loaded, "network weights not uploaded (uttt_upload_weights)");
     if (evaluator == UTTT_EVAL_NET_FP32) {
         if (ev3) cudaEventRecord(ev3[0], s);
-        UTTT_CUDA_OK(launch_trunk_fp32(e->w, e->tp.nn_planes, count, max_rows, e->act_a, e->act_b, s));
+        UTTT_CUDA_OK(launch_trunk_fp32(e->w, b.nn_planes, count, max_rows, b.act_a, b.act_b, s));
         e->prof_launches[1] += 1 + 2 * NET_BLOCKS;
     } else if (evaluator == UTTT_EVAL_NET_BF16) {
         // conv_input is accounted to the tree/gather share; the trunk events bracket trunk_tc_kernel alone
-        UTTT_CUDA_OK(launch_conv_input(e->w, e->tp.nn_planes, count, max_rows, e->act_a, s));
+        UTTT_CUDA_OK(launch_conv_input(e->w, b.nn_planes, count, max_rows, b.act_a, s));
         e->prof_launches[0] += 1;
         if (ev3) cudaEventRecord(ev3[0], s);
-        UTTT_CUDA_OK(launch_trunk_tc(e->w, e->act_a, count, max_rows, e->tc_resid, e->n_sm, s, e->tc_dbg));
+        UTTT_CUDA_OK(launch_trunk_tc(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
         e->prof_launches[1] += 1;
     } else {
         UTTT_CHECK(false, "evaluator %d cannot run on the device", evaluator);
     }
     if (ev3) cudaEventRecord(ev3[1], s);
-    UTTT_CUDA_OK(launch_heads(e->w, e->act_a, nullptr, count, max_rows, e->policy, e->value, 1, s));
+    UTTT_CUDA_OK(launch_heads(e->w, b.act_a, nullptr, count, max_rows, b.policy, b.value, 1, s));
     e->prof_launches[2] += 1;
     if (ev3) cudaEventRecord(ev3[2], s);
     return 0;
@@ -113,12 +139,15 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     UTTT_CHECK(cfg && out, "null argument");
     UTTT_CHECK(cfg->n_slots >= 1 && cfg->max_sims >= 1 && cfg->max_batch >= 1 && cfg->max_games >= 0,
                "bad config (n_slots=%d max_sims=%d max_batch=%d)", cfg->n_slots, cfg->max_sims, cfg->max_batch);
+    // node word limits: n in 16 bits, first_child in 20 bits, n_children (<= 81*batch) in 12 bits
+    UTTT_CHECK(cfg->max_sims <= 12000 && cfg->max_batch <= 50, "max_sims <= 12000 and max_batch <= 50 supported");
     if (uttt_device_check(cfg->device)) return 1;
     UTTT_CUDA_OK(cudaSetDevice(cfg->device));
     uttt_engine* e = new uttt_engine();
     memset(&e->tp, 0, sizeof(e->tp));
     memset(&e->w, 0, sizeof(e->w));
     e->cfg = *cfg;
+    e->lane_threshold = getenv("UTTT_LANE_THRESHOLD") ? atoi(getenv("UTTT_LANE_THRESHOLD")) : 1024;
     cudaDeviceProp prop;
     UTTT_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
     e->n_sm = prop.multiProcessorCount;
@@ -129,21 +158,25 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     TreeParams& t = e->tp;
     t.node_cap = e->node_cap;
     if (ealloc(e, &t.root, S) || ealloc(e, &t.leaf_state, S) || ealloc(e, &t.ctl, S) ||
-        ealloc(e, &t.path, S * PATH_CAP) || ealloc(e, &t.node_n, S * NC) || ealloc(e, &t.node_w, S * NC) ||
-        ealloc(e, &t.node_p, S * NC) || ealloc(e, &t.node_child, S * NC) || ealloc(e, &t.node_meta, S * NC) ||
+        ealloc(e, &t.path, S * PATH_CAP) || ealloc(e, &t.nodes, S * NC) ||
         ealloc(e, &t.nn_states, S) || ealloc(e, &t.nn_planes, S * 243 + 8) || ealloc(e, &t.nn_tree, S) ||
-        ealloc(e, &t.nn_k, S) || ealloc(e, &t.nn_count, 2) || ealloc(e, &t.out_counts, S * 81) ||
+        ealloc(e, &t.nn_k, S) || ealloc(e, &t.nn_count, 2 * N_LANES) || ealloc(e, &t.out_counts, S * 81) ||
         ealloc(e, &t.out_n, S) || ealloc(e, &t.counters, 8) || ealloc(e, &t.hist_states, G * 81) ||
         ealloc(e, &t.hist_counts, G * 81 * 81) || ealloc(e, &t.hist_actions, G * 81) || ealloc(e, &t.hist_len, G) ||
         ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
         ealloc(e, &e->act_a, S * 81 * 128) || ealloc(e, &e->act_b, S * 81 * 128) ||
-        ealloc(e, &e->tc_resid, (size_t)e->n_sm * 512 * 128) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128)) {
+        ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128)) {
         uttt_destroy(e);
         return 1;
     }
     UTTT_CUDA_OK(cudaMemset(t.ctl, 0, S * sizeof(TreeCtl)));
-    UTTT_CUDA_OK(cudaMemset(t.nn_count, 0, 2 * sizeof(int32_t)));
+    UTTT_CUDA_OK(cudaMemset(t.nn_count, 0, 2 * N_LANES * sizeof(int32_t)));
+    for (int i = 0; i < N_LANES; i++) {
+        UTTT_CUDA_OK(cudaStreamCreateWithFlags(&e->lane_stream[i], cudaStreamNonBlocking));
+        UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+    }
+    UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_counters, 8 * sizeof(unsigned long long)));
     UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_count, 2 * sizeof(int32_t)));
     for (int i = 0; i < EV_POOL; i++) UTTT_CUDA_OK(cudaEventCreate(&e->ev[i]));
@@ -166,6 +199,11 @@ int uttt_destroy(uttt_engine* e) {
     if (e->h_count) cudaFreeHost(e->h_count);
     for (int i = 0; i < EV_POOL; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
+    for (int i = 0; i < N_LANES; i++) {
+        if (e->lane_stream[i]) cudaStreamDestroy(e->lane_stream[i]);
+        if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+    }
+    if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     delete e;
     return 0;
 }
@@ -269,7 +307,7 @@ int uttt_net_forward(uttt_engine* e, const uint32_t* states_dev, int64_t n, int 
         int m = (int)((n - off < e->cfg.n_slots) ? (n - off) : e->cfg.n_slots);
         if (uttt_game_gather_planes(states_dev + off * 8, e->tp.nn_planes, m, s)) return 1;
         set_int_kernel<<<1, 1, 0, s>>>(e->fwd_count, m);
-        if (run_evaluator(e, mode, e->fwd_count, m, s, nullptr)) return 1;
+        if (run_evaluator(e, bufs_of(e, 0, 0), mode, e->fwd_count, m, s, nullptr)) return 1;
         UTTT_CUDA_OK(cudaMemcpyAsync(policy_dev + off * 81, e->policy, (size_t)m * 81 * sizeof(float),
                                      cudaMemcpyDeviceToDevice, s));
         UTTT_CUDA_OK(cudaMemcpyAsync(value_dev + off, e->value, (size_t)m * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -364,7 +402,7 @@ int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int
         for (; r < stop; r++) {
             t.parity = r & 1;
             UTTT_CUDA_OK(launch_tree_round(t, e->stream));
-            if (run_evaluator(e, evaluator, t.nn_count + t.parity, n_roots, e->stream, nullptr)) return 1;
+            if (run_evaluator(e, bufs_of(e, 0, 0), evaluator, t.nn_count + t.parity, n_roots, e->stream, nullptr)) return 1;
         }
         UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + ((r - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost,
                                      e->stream));
@@ -409,13 +447,42 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (n_games == 0) return 0;
     TreeParams& t = e->tp;
-    t.n_trees = n_trees; t.sims = sims; t.batch = batch; t.mode = MODE_SELFPLAY; t.flags = flags;
+    t.sims = sims; t.batch = batch; t.mode = MODE_SELFPLAY; t.flags = flags;
     t.parity = 0; t.row_stride = 1; t.copy_stride = 0;
     t.seed = seed; t.game0 = game0; t.n_games = n_games;
+    // Two lanes (halves of the slots) run on two streams: each lane is the sequential chain
+    // tree_round -> conv_input -> trunk -> heads, so one lane's tree/heads work runs in the shadow of the
+    // other lane's trunk (the tree blocks fit beside a trunk CTA on an SM).  Lanes share only the atomic
+    // game/progress counters and the history buffers (disjoint rows).
+    // (worth it only when half a batch still fills the machine; small batches are latency-bound)
+    const int n_lanes = (n_trees >= e->lane_threshold) ? N_LANES : 1;
+    TreeParams lane_tp[N_LANES];
+    EvalBufs lane_bufs[N_LANES];
+    int lane_trees[N_LANES];
+    for (int l = 0; l < n_lanes; l++) {
+        size_t first = (size_t)l * (size_t)(n_trees / n_lanes);
+        lane_trees[l] = (l == n_lanes - 1) ? n_trees - (int)first : n_trees / n_lanes;
+        TreeParams p = t;
+        p.n_trees = lane_trees[l];
+        p.root += first; p.leaf_state += first; p.ctl += first; p.path += first * PATH_CAP;
+        p.nodes += first * (size_t)e->node_cap;
+        p.nn_states += first; p.nn_planes += first * 243; p.nn_tree += first; p.nn_k += first;
+        p.nn_count += 2 * l;
+        p.policy = e->policy + first * e->cfg.max_batch * 81;
+        p.value = e->value + first * e->cfg.max_batch;
+        lane_tp[l] = p;
+        lane_bufs[l] = bufs_of(e, first, l);
+    }
     UTTT_CUDA_OK(cudaMemsetAsync(t.counters, 0, 8 * sizeof(unsigned long long), s));
     UTTT_CUDA_OK(cudaMemsetAsync(t.hist_len, 0, (size_t)n_games * sizeof(int32_t), s));
-    UTTT_CUDA_OK(launch_tree_begin(t, s));
-    e->prof_launches[0] += 1;
+    UTTT_CUDA_OK(cudaEventRecord(e->ev_fork, s));
+    cudaStream_t ls[N_LANES];
+    for (int l = 0; l < n_lanes; l++) {
+        ls[l] = (n_lanes == 1) ? s : e->lane_stream[l];
+        if (n_lanes > 1) UTTT_CUDA_OK(cudaStreamWaitEvent(ls[l], e->ev_fork, 0));
+        UTTT_CUDA_OK(launch_tree_begin(lane_tp[l], ls[l]));
+        e->prof_launches[0] += 1;
+    }
     // every round retires >= 1 simulation of every live slot: hard upper bound on rounds
     int64_t waves = (n_games + n_trees - 1) / n_trees;
     int64_t max_rounds = waves * 82 * (int64_t)(sims + 1) + CHECK_EVERY;
@@ -424,26 +491,41 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     while (!done && r < max_rounds) {
         int in_window = 0;
         for (; in_window < CHECK_EVERY; in_window++, r++) {
-            cudaEvent_t* ev = e->ev + 4 * in_window;
-            t.parity = (int)(r & 1);
-            cudaEventRecord(ev[0], s);
-            UTTT_CUDA_OK(launch_tree_round(t, s));
-            e->prof_launches[0] += 1;
-            if (run_evaluator(e, evaluator, t.nn_count + t.parity, n_trees, s, ev + 1)) return 1;
+            for (int l = 0; l < n_lanes; l++) {
+                cudaEvent_t* ev = e->ev + 4 * (in_window * N_LANES + l);
+                lane_tp[l].parity = (int)(r & 1);
+                cudaEventRecord(ev[0], ls[l]);
+                UTTT_CUDA_OK(launch_tree_round(lane_tp[l], ls[l]));
+                e->prof_launches[0] += 1;
+                if (run_evaluator(e, lane_bufs[l], evaluator, lane_tp[l].nn_count + lane_tp[l].parity, lane_trees[l],
+                                  ls[l], ev + 1))
+                    return 1;
+            }
         }
-        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-        UTTT_CUDA_OK(cudaStreamSynchronize(s));
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                     ls[0]));
+        for (int l = 0; l < n_lanes; l++) UTTT_CUDA_OK(cudaStreamSynchronize(ls[l]));
         for (int i = 0; i < in_window; i++) {
-            float ms = 0.f;
-            cudaEvent_t* ev = e->ev + 4 * i;
-            cudaEventElapsedTime(&ms, ev[0], ev[1]); e->prof_ms[0] += ms;
-            cudaEventElapsedTime(&ms, ev[1], ev[2]); e->prof_ms[1] += ms;
-            cudaEventElapsedTime(&ms, ev[2], ev[3]); e->prof_ms[2] += ms;
-            cudaEventElapsedTime(&ms, ev[0], ev[3]); e->prof_ms[3] += ms;
+            for (int l = 0; l < n_lanes; l++) {
+                float ms = 0.f;
+                cudaEvent_t* ev = e->ev + 4 * (i * N_LANES + l);
+                cudaEventElapsedTime(&ms, ev[0], ev[1]); e->prof_ms[0] += ms;
+                cudaEventElapsedTime(&ms, ev[1], ev[2]); e->prof_ms[1] += ms;
+                cudaEventElapsedTime(&ms, ev[2], ev[3]); e->prof_ms[2] += ms;
+                cudaEventElapsedTime(&ms, ev[0], ev[3]); e->prof_ms[3] += ms;
+            }
         }
         UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
+        // lane 0's copy may predate lane 1's last rounds: "done" only ever lags, never leads
         done = (int64_t)e->h_counters[1] >= n_games;
     }
+    if (n_lanes > 1) {          // join: the caller's stream continues after both lanes
+        for (int l = 0; l < n_lanes; l++) {
+            UTTT_CUDA_OK(cudaEventRecord(e->ev_join[l], ls[l]));
+            UTTT_CUDA_OK(cudaStreamWaitEvent(s, e->ev_join[l], 0));
+        }
+    }
+    UTTT_CUDA_OK(cudaMemcpy(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     UTTT_CHECK(done, "self-play did not finish within %lld rounds", (long long)max_rounds);
     e->prof_launches[3] = e->prof_launches[0] + e->prof_launches[1] + e->prof_launches[2];
     if (stats) {

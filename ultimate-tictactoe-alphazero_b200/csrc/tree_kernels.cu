@@ -18,8 +18,10 @@
 // loop is therefore equivalent to: evaluate the leaf once, append k copies of its child list,
 // back the value up k times sequentially.  That equivalent form is what runs here, and
 // oracle/uttt_oracle.c (which restates the literal queue/flush loop) checks it bit for bit.
-// Children store only (n, w, p, action): positions are recomputed by next_state() during the
-// descent, so a node costs 20 B instead of the reference's ~760 B.
+// A node is ONE 16-byte word {n:16 | action:7, w (f32), p (f32), first_child:20 | n_children:12}: positions are
+// recomputed by next_state() during the descent (the reference stores ~760 B per node), and a PUCT step
+// is a single coalesced 128-bit load per child -- the chosen child's own word already carries where its
+// children are, so the descent pays one L2 round trip per level.
 //
 // All float arithmetic on n/w/p uses explicit round-to-nearest intrinsics in the reference's
 // operation order (no FMA contraction, no reassociation): cpp/setup.py:10 builds with -O3 only.
@@ -31,20 +33,22 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int WARPS_PER_BLOCK = 4;
 
 struct TreeView {
-    int32_t* n;
-    float* w;
-    float* p;
-    uint32_t* child;
-    uint32_t* meta;
-    int32_t* path;
+    uint4* node;     // [node_cap]
+    int32_t* path;   // [PATH_CAP]
 };
 
 __device__ __forceinline__ TreeView view_of(const TreeParams& P, int t) {
-    size_t off = (size_t)t * (size_t)P.node_cap;
-    TreeView v = {P.node_n + off, P.node_w + off, P.node_p + off, P.node_child + off, P.node_meta + off,
-                  P.path + (size_t)t * PATH_CAP};
+    TreeView v = {P.nodes + (size_t)t * (size_t)P.node_cap, P.path + (size_t)t * PATH_CAP};
     return v;
 }
+
+__device__ __forceinline__ uint4 make_node(int action, float p) {
+    return make_uint4((uint32_t)action << 16, 0u, __float_as_uint(p), 0u);
+}
+__device__ __forceinline__ int node_n(const uint4& q) { return (int)(q.x & 0xFFFFu); }
+__device__ __forceinline__ int node_action(const uint4& q) { return (int)(q.x >> 16); }
+__device__ __forceinline__ uint32_t node_base(const uint4& q) { return q.w & 0xFFFFFu; }
+__device__ __forceinline__ int node_cnt(const uint4& q) { return (int)(q.w >> 20); }
 
 __device__ __forceinline__ PackedState warp_load_state(const PackedState* p, int lane) {
     uint32_t x = (lane < 8) ? reinterpret_cast<const uint32_t*>(p)[lane] : 0u;
@@ -65,19 +69,9 @@ __device__ void init_root(const TreeParams& P, const TreeView& T, TreeCtl& c, co
     uint32_t lm[3];
     int L = legal_mask(rs, lm);
     float pu = (L > 0) ? __fdiv_rn(1.0f, (float)L) : 0.0f;
-    if (lane == 0) {
-        T.n[0] = 0; T.w[0] = 0.0f; T.p[0] = 0.0f;
-        T.child[0] = (L > 0) ? 1u : 0u;
-        T.meta[0] = ((uint32_t)L << 8) | 0x7Fu;
-    }
-    for (int a = lane; a < 81; a += 32) {
-        if (legal_bit(lm, a)) {
-            int idx = 1 + legal_rank(lm, a);
-            T.n[idx] = 0; T.w[idx] = 0.0f; T.p[idx] = pu;
-            T.child[idx] = 0u;
-            T.meta[idx] = (uint32_t)a;
-        }
-    }
+    if (lane == 0) T.node[0] = make_uint4(0x7Fu << 16, 0u, 0u, (L > 0 ? 1u : 0u) | ((uint32_t)L << 20));
+    for (int a = lane; a < 81; a += 32)
+        if (legal_bit(lm, a)) T.node[1 + legal_rank(lm, a)] = make_node(a, pu);
     c.n_nodes = 1 + L;
     c.n_root = L;
     c.sims_left = P.sims;
@@ -91,13 +85,16 @@ __device__ void backup(const TreeView& T, int plen, int k, const float* vals, in
     for (int i = lane; i < plen; i += 32) {
         int node = T.path[i];
         bool flip = ((plen - 1 - i) & 1) != 0;
-        float w = T.w[node];
+        uint2* nw = reinterpret_cast<uint2*>(T.node + node);     // {n|action, w}
+        uint2 q = *nw;
+        float w = __uint_as_float(q.y);
         for (int c = 0; c < k; c++) {
             float v = vals ? vals[(size_t)c * vstride] : v_single;
             w = __fadd_rn(w, flip ? -v : v);
         }
-        T.w[node] = w;
-        T.n[node] += k;
+        q.y = __float_as_uint(w);
+        q.x += (uint32_t)k;                                       // n lives in the low 16 bits
+        *nw = q;
     }
     __syncwarp();
 }
@@ -135,20 +132,12 @@ __device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, i
             if (legal_bit(lm, a)) {
                 float pr = (sum > 0.0f) ? __fdiv_rn(__ldg(pol + a), sum) : uni;     // :155-163
                 int r = legal_rank(lm, a);
-                for (int q = 0; q < reps; q++) {
-                    int idx = base + (cp + q) * L + r;
-                    T.n[idx] = 0; T.w[idx] = 0.0f; T.p[idx] = pr;
-                    T.child[idx] = 0u;
-                    T.meta[idx] = (uint32_t)a;
-                }
+                for (int q = 0; q < reps; q++) T.node[base + (cp + q) * L + r] = make_node(a, pr);
             }
         }
         if (P.copy_stride == 0) break;
     }
-    if (lane == 0) {
-        T.child[leaf] = (uint32_t)base;
-        T.meta[leaf] = (T.meta[leaf] & 0xFFu) | ((uint32_t)(k * L) << 8);
-    }
+    if (lane == 0) T.node[leaf].w = (uint32_t)base | ((uint32_t)(k * L) << 20);
     c.n_nodes = base + k * L;
     backup(T, plen, k, P.value + row, P.copy_stride, 0.0f, lane);
     c.sims_left -= k;
@@ -160,14 +149,14 @@ __device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, i
 __device__ int sample_move(const TreeParams& P, const TreeView& T, const TreeCtl& c, const uint32_t lm[3], int lane) {
     int L = c.n_root;
     int tot = 0;
-    for (int i = lane; i < L; i += 32) tot += T.n[1 + i];
+    for (int i = lane; i < L; i += 32) tot += node_n(T.node[1 + i]);
     tot = __reduce_add_sync(FULL, tot);
     Philox4 r = philox4x32(P.seed, 1u, (uint32_t)c.game, (uint32_t)(c.game >> 32), (uint32_t)c.ply, 0u);
     uint32_t pick = __umulhi(r.x, (uint32_t)tot);
     int carry = 0, chosen = -1;
     for (int base = 0; base < L && chosen < 0; base += 32) {
         int i = base + lane;
-        int v = (i < L) ? T.n[1 + i] : 0;
+        int v = (i < L) ? node_n(T.node[1 + i]) : 0;
         int incl = v;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -239,7 +228,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
         if (c.sims_left <= 0) {
             // ---------------- the move is decided: root visit counts (cpp/uttt_mcts.cpp:177-180)
             if (P.mode == MODE_SEARCH) {
-                for (int i = lane; i < c.n_root; i += 32) P.out_counts[(size_t)t * 81 + i] = T.n[1 + i];
+                for (int i = lane; i < c.n_root; i += 32) P.out_counts[(size_t)t * 81 + i] = node_n(T.node[1 + i]);
                 if (lane == 0) P.out_n[t] = c.n_root;
                 c.phase = PHASE_DONE;
                 break;
@@ -249,7 +238,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
             size_t hrow = (size_t)c.game_idx * 81 + (size_t)c.ply;
             warp_store_state(P.hist_states + hrow, root, lane);
             for (int a = lane; a < 81; a += 32)
-                P.hist_counts[hrow * 81 + a] = legal_bit(lm, a) ? (uint16_t)T.n[1 + legal_rank(lm, a)] : (uint16_t)0;
+                P.hist_counts[hrow * 81 + a] = legal_bit(lm, a) ? (uint16_t)node_n(T.node[1 + legal_rank(lm, a)]) : (uint16_t)0;
             int action = sample_move(P, T, c, lm, lane);
             if (lane == 0) P.hist_actions[hrow] = (uint8_t)action;
             PackedState nx;
@@ -284,40 +273,54 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
         PackedState st = root;
         int node = 0, plen = 1;
         if (lane == 0) T.path[0] = 0;
+        uint32_t link = T.node[0].w;               // first_child | n_children<<20 of the current node
         bool terminal = false, lost = false;
         uint32_t lm[3];
         for (;;) {
             int L = legal_mask(st, lm);
             lost = is_lose(st);
             if (lost || L == 0) { terminal = true; break; }
-            uint32_t cbase = T.child[node];
+            const uint32_t cbase = link & 0xFFFFFu;
             if (cbase == 0u) break;                                  // unexpanded leaf
-            int cnt = (int)(T.meta[node] >> 8);
-            // PUCT, cpp/uttt_mcts.cpp:57-81
+            const int cnt = (int)(link >> 20);
+            const uint4* ch = T.node + cbase;
+            // PUCT, cpp/uttt_mcts.cpp:57-81.  Children are read once (one 128-bit load each); lanes keep their
+            // first three children in registers, longer lists (k-fold duplicated, Q-M3) re-read through L1.
+            uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0, c2 = c0;
             int tot = 0;
-            for (int i = lane; i < cnt; i += 32) tot += T.n[cbase + i];
+            if (lane < cnt) { c0 = ch[lane]; tot += node_n(c0); }
+            if (lane + 32 < cnt) { c1 = ch[lane + 32]; tot += node_n(c1); }
+            if (lane + 64 < cnt) { c2 = ch[lane + 64]; tot += node_n(c2); }
+            for (int i = lane + 96; i < cnt; i += 32) tot += node_n(ch[i]);
             tot = __reduce_add_sync(FULL, tot);
-            float sq = __fsqrt_rn((float)tot);
+            const float sq = __fsqrt_rn((float)tot);
             float best = -1e9f;
             int besti = 0x7FFFFFFF;
-            for (int i = lane; i < cnt; i += 32) {
-                int n = T.n[cbase + i];
-                float w = T.w[cbase + i], p = T.p[cbase + i];
-                float q = (n > 0) ? __fdiv_rn(-w, (float)n) : 0.0f;
+            uint32_t bestx = 0u, bestlink = 0u;
+            auto consider = [&](const uint4& q, int i) {
+                int n = node_n(q);
+                float w = __uint_as_float(q.y), p = __uint_as_float(q.z);
+                float qv = (n > 0) ? __fdiv_rn(-w, (float)n) : 0.0f;
                 float u = __fdiv_rn(__fmul_rn(p, sq), (float)(1 + n));
-                float s = __fadd_rn(q, u);
-                if (s > best) { best = s; besti = i; }
-            }
+                float s = __fadd_rn(qv, u);
+                if (s > best) { best = s; besti = i; bestx = q.x; bestlink = q.w; }
+            };
+            if (lane < cnt) consider(c0, lane);
+            if (lane + 32 < cnt) consider(c1, lane + 32);
+            if (lane + 64 < cnt) consider(c2, lane + 64);
+            for (int i = lane + 96; i < cnt; i += 32) consider(ch[i], i);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {                 // first maximum wins (Q-M6)
                 float ob = __shfl_xor_sync(FULL, best, off);
                 int oi = __shfl_xor_sync(FULL, besti, off);
-                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                uint32_t ox = __shfl_xor_sync(FULL, bestx, off);
+                uint32_t ol = __shfl_xor_sync(FULL, bestlink, off);
+                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; bestx = ox; bestlink = ol; }
             }
             node = (int)cbase + besti;
-            int action = (int)(T.meta[node] & 0xFFu);
+            link = bestlink;
             PackedState nx;
-            next_state(st, action, nx);
+            next_state(st, (int)(bestx >> 16), nx);
             st = nx;
             if (lane == 0) T.path[plen] = node;
             plen++;
