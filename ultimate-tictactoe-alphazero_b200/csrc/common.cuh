@@ -122,10 +122,15 @@ cudaError_t launch_trunk_fp32(const NetWeights& w, const __nv_bfloat16* planes, 
                               float* act_a, float* act_b, cudaStream_t s);
 // act: in = conv_input output, out = trunk output (fp32 [rows][81][128]); resid: [ceil(rows/5)][512][128] fp32
 cudaError_t launch_trunk_tc(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* resid,
-                            int n_sm, cudaStream_t s, long long* dbg = nullptr);
+                            int n_sm, cudaStream_t s, long long* dbg = nullptr, int min_count = 0);
 cudaError_t launch_heads(const NetWeights& w, const float* act_f32, const __nv_bfloat16* act_bf16,
                          const int32_t* count, int max_rows, float* policy, float* value, int row_stride,
                          cudaStream_t s);
+// cluster-of-2 variant (net_tc2.cu): one group of positions per CTA pair; skip: [n_sm][16][256] fp16x8
+cudaError_t launch_trunk_tc2(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* skip,
+                             int n_sm, cudaStream_t s, long long* dbg = nullptr);
+cudaError_t trunk_tc2_init();
+int trunk_tc2_capacity(int n_sm);    // largest batch the cluster variant evaluates in one wave
 int trunk_tc_smem_bytes();
 cudaError_t trunk_tc_init();
 

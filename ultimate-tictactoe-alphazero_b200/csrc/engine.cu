@@ -50,6 +50,7 @@ struct uttt_engine {
     int32_t* fwd_count;     // device int for uttt_net_forward
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0 (diagnostics)
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
+    int trunk_variant;      // 1: one CTA per group (net_tc.cu), 2: CTA pair per group (net_tc2.cu)
     NetWeights w;
     unsigned long long* h_counters;   // pinned [8]
     int32_t* h_count;                 // pinned [2]
@@ -111,7 +112,19 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         UTTT_CUDA_OK(launch_conv_input(e->w, b.nn_planes, count, max_rows, b.act_a, s));
         e->prof_launches[0] += 1;
         if (ev3) cudaEventRecord(ev3[0], s);
-        UTTT_CUDA_OK(launch_trunk_tc(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+        // Two trunk variants are enqueued; each reads the queue length on the device and exits at once if the
+        // batch is not in its range: small batches (one wave of CTA pairs) are latency-bound -> cluster variant,
+        // larger ones are throughput-bound -> one CTA per group with 4 accumulator tiles.
+        if (e->trunk_variant == 2) {
+            if (max_rows > trunk_tc2_capacity(e->n_sm)) {
+                UTTT_CUDA_OK(launch_trunk_tc(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
+                                             trunk_tc2_capacity(e->n_sm)));
+                e->prof_launches[1] += 1;
+            }
+            UTTT_CUDA_OK(launch_trunk_tc2(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+        } else {
+            UTTT_CUDA_OK(launch_trunk_tc(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+        }
         e->prof_launches[1] += 1;
     } else {
         UTTT_CHECK(false, "evaluator %d cannot run on the device", evaluator);
@@ -147,6 +160,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     memset(&e->tp, 0, sizeof(e->tp));
     memset(&e->w, 0, sizeof(e->w));
     e->cfg = *cfg;
+    e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 2;
     e->lane_threshold = getenv("UTTT_LANE_THRESHOLD") ? atoi(getenv("UTTT_LANE_THRESHOLD")) : 1024;
     cudaDeviceProp prop;
     UTTT_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -293,6 +307,7 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
     if (!W.res_w_bf16) UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_bf16, r_h.size() * sizeof(__nv_bfloat16)));
     UTTT_CUDA_OK(cudaMemcpy(W.res_w_bf16, r_h.data(), r_h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     UTTT_CUDA_OK(trunk_tc_init());
+    UTTT_CUDA_OK(trunk_tc2_init());
     W.loaded = true;
     return 0;
 }

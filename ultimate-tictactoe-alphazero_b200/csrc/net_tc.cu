@@ -173,10 +173,12 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
                 float* resid,                           // [gridDim][16 panels][512 rows][8] fp16 skip connection (L2-resident)
                 const int32_t* __restrict__ count,
+                int min_count,                          // batches up to this size are handled by trunk_tc2_kernel
                 long long* dbg) {                       // optional [32][4] clock64 timeline of CTA 0 (diagnostics)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pos = *count;
+    if (n_pos <= min_count) return;
     // positions per group: as few as keeps every group in the first wave (latency matters when the batch is
     // small), at most 5; 4 positions would need the same 4 tiles as 5, so it is never chosen.
     int P = (n_pos + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -404,10 +406,10 @@ cudaError_t trunk_tc_init() {
 }
 
 cudaError_t launch_trunk_tc(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* resid,
-                            int n_sm, cudaStream_t s, long long* dbg) {
+                            int n_sm, cudaStream_t s, long long* dbg, int min_count) {
     int grid = max_rows < n_sm ? max_rows : n_sm;
     if (grid < 1) grid = 1;
-    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.res_b, act, resid, count, dbg);
+    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.res_b, act, resid, count, min_count, dbg);
     return cudaGetLastError();
 }
 

@@ -1,0 +1,468 @@
+// net_tc2.cu -- trunk_tc2_kernel: the residual trunk as a tcgen05 implicit GEMM where a thread-block
+// CLUSTER of two CTAs (two SMs) shares one group of positions, split by GEMM rows.
+//
+// Same math and layouts as trunk_tc_kernel (net_tc.cu: padded 100-row positions, no-swizzle K-major A panels
+// resident in shared memory, bulk-copied pre-packed weights, TMEM accumulators, in-place epilogue), but the
+// up-to-4 accumulator tiles of a group are divided between the two CTAs of a cluster (2+2, 2+1, 1+1 or 1+0).
+// Per CTA that halves the serial work of a forward pass -- the self-play rounds are latency-bound at the
+// reference's 500-game cycle (about 345 queued leaves per round = 69 groups of 5: one CTA per group would
+// use 69 of 148 SMs, a CTA pair per group uses 138) -- and frees shared memory for an 8-stage weight ring.
+//
+// The only coupling between the two CTAs is the 11-row halo of the 3x3 taps at the split:
+//   * the epilogue warp that owns the last 11 rows of rank 0 (first 11 rows of rank 1) also stores them into
+//     the peer's lead (tail) margin through distributed shared memory (st.shared::cluster), then arrives on the
+//     peer's act_ready barrier of its boundary tile (mbarrier.arrive.release.cluster on a mapa address);
+//   * before it overwrites the peer's margin it waits until the peer's boundary-tile MMAs of the current
+//     layer have retired: the peer's issuer signals that with a multicast tcgen05.commit onto the
+//     `bnd_accum` barrier of THIS CTA.
+// Everything else (weights, accumulators, skip connection, barriers) is CTA-private.
+//
+// Warp roles (19 warps): 0-15 epilogue (2 tiles x 4 TMEM lane quarters x 2 column halves -- the epilogue is
+// instruction-latency bound, so it wants warps, not wider threads), 16 weight producer, 17-18 MMA issuers.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace uttt {
+namespace tc2 {
+
+constexpr int POS_ROWS = 100;
+constexpr int MAX_P = 5;
+constexpr int LOC_TILES = 2;                    // accumulator tiles per CTA
+constexpr int LEAD = 11;
+constexpr int AROWS = 280;                      // >= LEAD + 256 + 11
+constexpr int PANEL_BYTES = AROWS * 16;
+constexpr int A_BYTES = 16 * PANEL_BYTES;       // 71,680
+constexpr int STAGE_BYTES = 16384;
+constexpr int STAGES = 8;
+constexpr int STAGES_PER_LAYER = 18;
+constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
+constexpr int SMEM_BYTES = BAR_OFF + 256;
+constexpr int EPI_WARPS = 8 * LOC_TILES;         // (tile, lane quarter, column half)
+constexpr int THREADS = (EPI_WARPS + 1 + LOC_TILES) * 32;      // 608
+constexpr int SKIP_ROWS = 128 * LOC_TILES;
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, const uint4& v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// bounded wait; traps instead of hanging.  CLUSTER = true acquires at cluster scope (needed where an arrival
+// comes from the peer CTA); ptxas then flushes L1 after the wait (CCTL.IVALL), so it is used only there.
+template <bool CLUSTER = false>
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    for (uint32_t it = 0;; it++) {
+        if (CLUSTER)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        else
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        if (ok) return;
+        if (backoff_ns) __nanosleep(backoff_ns);
+        if ((it & 1023u) == 1023u) {
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ll) {
+                printf("uttt trunk_tc2: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+                       threadIdx.x, bar, parity);
+                __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(fminf(lo, 65504.0f), fminf(hi, 65504.0f));
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void f16x8_add(const uint4& q, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float2 f = __half22float2(h[i]);
+        v[2 * i] += f.x;
+        v[2 * i + 1] += f.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+    return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ uint4 pack8_f16(const float* v) {
+    return make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+}
+// ReLU fused into the conversion (F2FP.RELU): max(x,0) then round to bf16 / fp16 (saturating)
+__device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t relu_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint4 relu_pack8_bf16(const float* v) {
+    return make_uint4(relu_bf16x2(v[0], v[1]), relu_bf16x2(v[2], v[3]), relu_bf16x2(v[4], v[5]), relu_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ uint4 relu_pack8_f16(const float* v) {
+    return make_uint4(relu_f16x2(v[0], v[1]), relu_f16x2(v[2], v[3]), relu_f16x2(v[4], v[5]), relu_f16x2(v[6], v[7]));
+}
+// v[0..7] += 8 fp16 values (FADD2 pairs)
+__device__ __forceinline__ void f16x8_add2(const uint4& q, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+    float2* v2 = reinterpret_cast<float2*>(v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) v2[i] = __fadd2_rn(v2[i], __half22float2(h[i]));
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
+                 const float* __restrict__ bias,         // [32][128]
+                 float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
+                 uint4* skip,                            // [gridDim][16 panels][256 rows] fp16x8 skip connection
+                 const int32_t* __restrict__ count,
+                 int max_count,                          // batches above this are left to trunk_tc_kernel
+                 long long* dbg) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const int n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+    const int n_pos = *count;
+    if (n_pos > max_count) return;
+    int P = (n_pos + n_pairs - 1) / n_pairs;
+    P = P < 1 ? 1 : (P >= 4 ? MAX_P : P);
+    const int T = (P * POS_ROWS + 127) / 128;         // tiles of the pair: 1..4
+    const int T0 = (T + 1) >> 1;                      // rank 0 takes the first ceil(T/2) tiles
+    const int tiles = (rank == 0) ? T0 : T - T0;      // this CTA's tiles (0..2)
+    const int tile0 = (rank == 0) ? 0 : T0;           // first global tile of this CTA
+    const int n_groups = (n_pos + P - 1) / P;
+    if (pair >= n_groups) return;                     // both CTAs of the pair take the same branch
+    const bool has_peer = (T - T0) > 0;
+
+    uint8_t* sA = smem;
+    const uint32_t sA_u = smem_u32(sA);
+    const uint32_t sB_u = sA_u + A_BYTES;
+    const uint32_t bar_u = sA_u + BAR_OFF;
+    // barriers: full[8] @0, empty[8] @64, accum[2] @128, act[2] @144, bnd_accum @160; tmem holder @168
+    const uint32_t bar_full = bar_u, bar_empty = bar_u + 64, bar_accum = bar_u + 128, bar_act = bar_u + 144,
+                   bar_bnd = bar_u + 160;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 168);
+    // the tile of this CTA that touches the peer's rows, and the quarter-warp that owns the shared rows
+    const int bnd_tile = (rank == 0) ? tiles - 1 : 0;
+    const int bnd_quarter = (rank == 0) ? 3 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, tiles > 0 ? tiles : 1); }
+        for (int t = 0; t < LOC_TILES; t++) {
+            mbar_init(bar_accum + 8 * t, 1);
+            int c = 8 + (t > 0 ? 2 : 0) + (t < tiles - 1 ? 2 : 0) + ((has_peer && t == bnd_tile) ? 2 : 0);
+            mbar_init(bar_act + 8 * t, c);
+        }
+        mbar_init(bar_bnd, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == EPI_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                     "r"(256u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+    fence_async_all();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // the peer's barriers and margins exist before anyone signals them
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    const uint32_t peer = rank ^ 1u;
+
+    int iter = 0;
+    for (int g = pair; g < n_groups; g += n_pairs, iter++) {
+        if (warp < EPI_WARPS) {
+            // ================= epilogue warps: (tile, TMEM lane quarter, 64-column half) =================
+            const int lt = warp >> 3, quarter = warp & 3, chalf = (warp >> 2) & 1;
+            if (lt >= tiles) continue;
+            const int lr = lt * 128 + quarter * 32 + lane;            // local GEMM row
+            const int gr = tile0 * 128 + lr;                          // row within the group
+            const int pos = gr / POS_ROWS, idx = gr - pos * POS_ROWS;
+            const int r = idx / 10, c = idx - 10 * r;
+            const int gpos = g * P + pos;
+            const bool valid = (pos < P) && (r < 9) && (c < 9) && (gpos < n_pos);
+            float* arow = act + ((size_t)gpos * 81 + (size_t)(r * 9 + c)) * 128 + chalf * 64;
+            uint4* srow_skip = skip + (size_t)blockIdx.x * (16 * SKIP_ROWS) + (size_t)(chalf * 8) * SKIP_ROWS + (size_t)lr;
+            uint8_t* srow = sA + (size_t)(chalf * 8) * PANEL_BYTES + (size_t)(LEAD + lr) * 16;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lt * 128 + chalf * 64);
+            const bool nb_lo = (quarter == 0) && (lt > 0);
+            const bool nb_hi = (quarter == 3) && (lt < tiles - 1);
+            const bool bnd = has_peer && (lt == bnd_tile) && (quarter == bnd_quarter);
+            // rows this thread mirrors into the peer's margin: rank 0 lanes 21..31 -> peer lead rows 0..10,
+            // rank 1 lanes 0..10 -> peer tail rows (LEAD + 128*T0 + lane)
+            const bool mirror = bnd && ((rank == 0) ? (lane >= 21) : (lane < 11));
+            const uint32_t peer_row = (rank == 0) ? (uint32_t)(lane - 21) : (uint32_t)(LEAD + 128 * T0 + lane);
+            const uint32_t peer_srow = map_to_rank(sA_u + (uint32_t)(chalf * 8) * PANEL_BYTES + peer_row * 16u, peer);
+            const uint32_t peer_act = map_to_rank(bar_act + 8 * ((rank == 0) ? 0 : (T0 - 1)), peer);
+            const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+            // prologue: conv_input output -> fp16 skip buffer + bf16 A operand of layer 0
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ch++) {
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    float4 x = valid ? reinterpret_cast<const float4*>(arow + ch * 16)[j] : make_float4(0, 0, 0, 0);
+                    v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    uint4 pk = pack8_bf16(v + 8 * j);
+                    *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = pk;
+                    if (mirror) st_cluster_v4(peer_srow + (uint32_t)(ch * 2 + j) * PANEL_BYTES, pk);
+                    if (valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = pack8_f16(v + 8 * j);
+                }
+            }
+            fence_async_all();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_act + 8 * lt);
+                if (nb_lo) mbar_arrive(bar_act + 8 * (lt - 1));
+                if (nb_hi) mbar_arrive(bar_act + 8 * (lt + 1));
+                if (bnd) mbar_arrive_remote(peer_act);
+            }
+
+#pragma unroll 1
+            for (int layer = 0; layer < NET_LAYERS; layer++) {
+                const uint32_t lpar = (uint32_t)((iter * NET_LAYERS + layer) & 1);
+                const bool second = (layer & 1) != 0;
+                const bool last = (layer == NET_LAYERS - 1);
+                // the skip connection (8 x 16 B per thread) is fetched from L2 while the MMAs still run
+                uint4 sk[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) sk[j] = (second && valid) ? srow_skip[(size_t)j * SKIP_ROWS] : zero4;
+                mbar_wait(bar_accum + 8 * lt, lpar, 128);
+                if (nb_lo) mbar_wait(bar_accum + 8 * (lt - 1), lpar, 64);
+                if (nb_hi) mbar_wait(bar_accum + 8 * (lt + 1), lpar, 64);
+                if (bnd) mbar_wait<true>(bar_bnd, lpar, 64);     // the peer's boundary-tile MMAs have retired
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 2] = clock64();
+                tc_fence_after();
+                const float* bl = bias + layer * 128 + chalf * 64;
+                float va[16], vb[16];
+                tmem_ld16(taddr, va);
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    float* v = (ch & 1) ? vb : va;
+                    tmem_ld_wait();
+                    if (ch < 3) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
+                    float2* v2 = reinterpret_cast<float2*>(v);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 16) + j);
+                        v2[2 * j] = __fadd2_rn(v2[2 * j], make_float2(b4.x, b4.y));
+                        v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(b4.z, b4.w));
+                    }
+                    f16x8_add2(sk[2 * ch], v);
+                    f16x8_add2(sk[2 * ch + 1], v + 8);
+                    if (last) {
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                reinterpret_cast<float4*>(arow + ch * 16)[j] =
+                                    make_float4(fmaxf(v[4 * j], 0.f), fmaxf(v[4 * j + 1], 0.f), fmaxf(v[4 * j + 2], 0.f), fmaxf(v[4 * j + 3], 0.f));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; j++) {
+                            uint4 pk = valid ? relu_pack8_bf16(v + 8 * j) : zero4;      // padding rows stay zero
+                            *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = pk;
+                            if (mirror) st_cluster_v4(peer_srow + (uint32_t)(ch * 2 + j) * PANEL_BYTES, pk);
+                            if (second && valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = relu_pack8_f16(v + 8 * j);
+                        }
+                    }
+                }
+                if (!last) {
+                    fence_async_all();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive(bar_act + 8 * lt);
+                        if (nb_lo) mbar_arrive(bar_act + 8 * (lt - 1));
+                        if (nb_hi) mbar_arrive(bar_act + 8 * (lt + 1));
+                        if (bnd) mbar_arrive_remote(peer_act);
+                    }
+                }
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 3] = clock64();
+            }
+            tc_fence_before();
+        } else if (warp == EPI_WARPS) {
+            // ================= weight producer =================
+            if (tiles == 0) continue;
+#pragma unroll 1
+            for (int n = 0; n < NET_LAYERS * STAGES_PER_LAYER; n++) {
+                const int gn = iter * NET_LAYERS * STAGES_PER_LAYER + n;
+                const int stage = gn % STAGES;
+                const uint32_t par = (uint32_t)((gn / STAGES) & 1);
+                mbar_wait(bar_empty + 8 * stage, par ^ 1u);
+                if (lane == 0) {
+                    mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+                    bulk_g2s(sB_u + stage * STAGE_BYTES, wq + (size_t)n * (STAGE_BYTES / 2), STAGE_BYTES, bar_full + 8 * stage);
+                }
+                __syncwarp();
+            }
+        } else {
+            // ================= MMA issuers: warp 9+t drives local accumulator tile t =================
+            const int lt = warp - (EPI_WARPS + 1);
+            if (lt >= tiles) continue;
+            const bool leader = elect_one();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(lt * 128);
+            const uint32_t a_tile = sA_u + (uint32_t)(LEAD + lt * 128) * 16u;
+            const bool signal_peer = has_peer && (lt == bnd_tile);
+#pragma unroll 1
+            for (int layer = 0; layer < NET_LAYERS; layer++) {
+                if (signal_peer) mbar_wait<true>(bar_act + 8 * lt, (uint32_t)((iter * NET_LAYERS + layer) & 1), 32);
+                else mbar_wait(bar_act + 8 * lt, (uint32_t)((iter * NET_LAYERS + layer) & 1), 32);
+                fence_async_all();
+                tc_fence_after();
+                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[layer * 4 + 0] = clock64();
+#pragma unroll 1
+                for (int s = 0; s < STAGES_PER_LAYER; s++) {
+                    const int gn = (iter * NET_LAYERS + layer) * STAGES_PER_LAYER + s;
+                    const int stage = gn % STAGES;
+                    const uint32_t par = (uint32_t)((gn / STAGES) & 1);
+                    mbar_wait(bar_full + 8 * stage, par);
+                    tc_fence_after();
+                    if (leader) {
+                        const int tap = s >> 1, half = s & 1;
+                        const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                        const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * PANEL_BYTES;
+                        const uint32_t b0 = sB_u + (uint32_t)stage * STAGE_BYTES;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * PANEL_BYTES, PANEL_BYTES, 128),
+                                      make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), IDESC, (uint32_t)((s | ks) != 0));
+                        }
+                        umma_commit(bar_empty + 8 * stage);
+                        if (s == STAGES_PER_LAYER - 1) {
+                            umma_commit(bar_accum + 8 * lt);
+                            if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
+                            if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0) dbg[layer * 4 + 1] = clock64();
+                        }
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                 // nobody exits while the peer may still write its margins / barriers
+    if (warp == EPI_WARPS + 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+}  // namespace tc2
+
+cudaError_t trunk_tc2_init() {
+    return cudaFuncSetAttribute(tc2::trunk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
+}
+
+int trunk_tc2_capacity(int n_sm) { return (n_sm / 2) * tc2::MAX_P; }
+
+cudaError_t launch_trunk_tc2(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* skip, int n_sm,
+                             cudaStream_t s, long long* dbg) {
+    int pairs = n_sm / 2;
+    if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
+    tc2::trunk_tc2_kernel<<<2 * pairs, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
+        w.res_w_bf16, w.res_b, act, reinterpret_cast<uint4*>(skip), count, trunk_tc2_capacity(n_sm), dbg);
+    return cudaGetLastError();
+}
+
+}  // namespace uttt
