@@ -28,6 +28,28 @@ constexpr int EV_POOL = CHECK_EVERY * 4 * N_LANES;
 
 __global__ void set_int_kernel(int32_t* p, int32_t v) { *p = v; }
 
+// BatchNorm folding + repacking of the 32 residual 3x3 convolutions on the device:
+// raw (32)(co,ci,ky,kx) fp32 + bn (32)(4)(128) -> fp32 [l][tap][ci][co], bias [l][co], bf16 [l][tap][ci/8][co][ci%8]
+__global__ void __launch_bounds__(256) pack_res_kernel(const float* __restrict__ raw, const float* __restrict__ bn,
+                                                       float* __restrict__ w32, float* __restrict__ b32,
+                                                       __nv_bfloat16* __restrict__ w16) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // index into raw
+    if (i >= (size_t)32 * 128 * 128 * 9) return;
+    int tap = (int)(i % 9);
+    size_t r = i / 9;
+    int ci = (int)(r % 128);
+    r /= 128;
+    int co = (int)(r % 128);
+    int l = (int)(r / 128);
+    const float* b = bn + (size_t)l * 4 * 128;
+    float g = b[co], beta = b[128 + co], m = b[256 + co], v = b[384 + co];
+    float sc = __fdiv_rn(g, __fsqrt_rn(__fadd_rn(v, 1e-5f)));
+    float val = __fmul_rn(raw[i], sc);
+    w32[(((size_t)l * 9 + tap) * 128 + ci) * 128 + co] = val;
+    w16[((((size_t)l * 9 + tap) * 16 + ci / 8) * 128 + co) * 8 + (ci % 8)] = __float2bfloat16(val);
+    if (ci == 0 && tap == 0) b32[l * 128 + co] = __fsub_rn(beta, __fmul_rn(m, sc));
+}
+
 template <typename T>
 cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
 
@@ -52,6 +74,8 @@ struct uttt_engine {
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
     int trunk_variant;      // 1: one CTA per group (net_tc.cu), 2: CTA pair per group (net_tc2.cu)
     NetWeights w;
+    float* raw_res;         // staging for the raw residual conv weights / bn of an upload
+    float* raw_res_bn;
     unsigned long long* h_counters;   // pinned [8]
     int32_t* h_count;                 // pinned [2]
     // step-wise search state
@@ -209,6 +233,8 @@ int uttt_destroy(uttt_engine* e) {
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b};
     for (float* p : wp) if (p) cudaFree(p);
+    if (e->raw_res) cudaFree(e->raw_res);
+    if (e->raw_res_bn) cudaFree(e->raw_res_bn);
     if (e->h_counters) cudaFreeHost(e->h_counters);
     if (e->h_count) cudaFreeHost(e->h_count);
     for (int i = 0; i < EV_POOL; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -250,14 +276,31 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
         else memcpy(v.data(), p, n * sizeof(float));
         return 0;
     };
-    std::vector<float> ciw, bni, rw, rbn, pcw, pbn, pfw, pfb, vcw, vbn, v1w, v1b, v2w, v2b;
+    std::vector<float> ciw, bni, pcw, pbn, pfw, pfb, vcw, vbn, v1w, v1b, v2w, v2b;
     if (fetch(w->conv_input_w, 128 * 27, ciw) || fetch(w->bn_input, 4 * 128, bni) ||
-        fetch(w->res_conv_w, (size_t)32 * 128 * 128 * 9, rw) || fetch(w->res_bn, (size_t)32 * 4 * 128, rbn) ||
         fetch(w->policy_conv_w, 2 * 128, pcw) || fetch(w->policy_bn, 8, pbn) || fetch(w->policy_fc_w, 81 * 162, pfw) ||
         fetch(w->policy_fc_b, 81, pfb) || fetch(w->value_conv_w, 128, vcw) || fetch(w->value_bn, 4, vbn) ||
         fetch(w->value_fc1_w, 256 * 81, v1w) || fetch(w->value_fc1_b, 256, v1b) || fetch(w->value_fc2_w, 256, v2w) ||
         fetch(w->value_fc2_b, 1, v2b))
         return 1;
+    UTTT_CHECK(w->res_conv_w && w->res_bn, "null weight tensor");
+
+    // the 32 residual convolutions (4.7 M weights) are folded and repacked by a kernel
+    const size_t n_res = (size_t)32 * 128 * 128 * 9, n_rbn = (size_t)32 * 4 * 128;
+    NetWeights& W = e->w;
+    if (!e->raw_res) {
+        UTTT_CUDA_OK(cudaMalloc((void**)&e->raw_res, n_res * sizeof(float)));
+        UTTT_CUDA_OK(cudaMalloc((void**)&e->raw_res_bn, n_rbn * sizeof(float)));
+        UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w, n_res * sizeof(float)));
+        UTTT_CUDA_OK(cudaMalloc((void**)&W.res_b, 32 * 128 * sizeof(float)));
+        UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_bf16, n_res * sizeof(__nv_bfloat16)));
+    }
+    cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res, w->res_conv_w, n_res * sizeof(float), kind, e->stream));
+    UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res_bn, w->res_bn, n_rbn * sizeof(float), kind, e->stream));
+    pack_res_kernel<<<ceil_div((int64_t)n_res, 256), 256, 0, e->stream>>>(e->raw_res, e->raw_res_bn, W.res_w, W.res_b,
+                                                                         W.res_w_bf16);
+    UTTT_CUDA_OK(cudaGetLastError());
 
     std::vector<float> sc, sh;
     // conv_input: (128,3,3,3) [co][ci][ky][kx] -> [tap][ci][co]
@@ -267,21 +310,6 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
         for (int ci = 0; ci < 3; ci++)
             for (int tap = 0; tap < 9; tap++)
                 ci_w[(tap * 3 + ci) * 128 + co] = ciw[(co * 3 + ci) * 9 + tap] * sc[co];
-    // residual convs: (32)(128,128,3,3) -> fp32 [layer][tap][ci][co] and bf16 [layer][tap][ci/8][co][ci%8]
-    std::vector<float> r_w((size_t)32 * 9 * 128 * 128), r_b(32 * 128);
-    std::vector<__nv_bfloat16> r_h((size_t)32 * 9 * 128 * 128);
-    for (int l = 0; l < 32; l++) {
-        bn_fold(rbn.data() + (size_t)l * 4 * 128, 128, sc, sh);
-        for (int co = 0; co < 128; co++) {
-            r_b[l * 128 + co] = sh[co];
-            for (int ci = 0; ci < 128; ci++)
-                for (int tap = 0; tap < 9; tap++) {
-                    float v = rw[(((size_t)l * 128 + co) * 128 + ci) * 9 + tap] * sc[co];
-                    r_w[(((size_t)l * 9 + tap) * 128 + ci) * 128 + co] = v;
-                    r_h[((((size_t)l * 9 + tap) * 16 + ci / 8) * 128 + co) * 8 + (ci % 8)] = __float2bfloat16(v);
-                }
-        }
-    }
     // heads
     bn_fold(pbn.data(), 2, sc, sh);
     std::vector<float> pc_w(256), pc_b(sh);
@@ -297,15 +325,12 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
     for (int j = 0; j < 256; j++)
         for (int i = 0; i < 81; i++) v1_t[i * 256 + j] = v1w[j * 81 + i];
 
-    NetWeights& W = e->w;
-    if (to_device(&W.conv_in_w, ci_w) || to_device(&W.conv_in_b, ci_b) || to_device(&W.res_w, r_w) ||
-        to_device(&W.res_b, r_b) || to_device(&W.pol_conv_w, pc_w) || to_device(&W.pol_conv_b, pc_b) ||
+    if (to_device(&W.conv_in_w, ci_w) || to_device(&W.conv_in_b, ci_b) || to_device(&W.pol_conv_w, pc_w) || to_device(&W.pol_conv_b, pc_b) ||
         to_device(&W.pol_fc_w, pf_t) || to_device(&W.pol_fc_b, pfb) || to_device(&W.val_conv_w, vc_w) ||
         to_device(&W.val_conv_b, vc_b) || to_device(&W.val_fc1_w, v1_t) || to_device(&W.val_fc1_b, v1b) ||
         to_device(&W.val_fc2_w, v2w) || to_device(&W.val_fc2_b, v2b))
         return 1;
-    if (!W.res_w_bf16) UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_bf16, r_h.size() * sizeof(__nv_bfloat16)));
-    UTTT_CUDA_OK(cudaMemcpy(W.res_w_bf16, r_h.data(), r_h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+    UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
     UTTT_CUDA_OK(trunk_tc_init());
     UTTT_CUDA_OK(trunk_tc2_init());
     W.loaded = true;

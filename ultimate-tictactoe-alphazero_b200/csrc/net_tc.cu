@@ -150,6 +150,23 @@ __device__ __forceinline__ void f16x8_add(const uint4& q, float* v) {
         v[2 * i + 1] += f.y;
     }
 }
+// ReLU fused into the conversion (F2FP.RELU); fp16 conversion saturates
+__device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t relu_f16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ void f16x8_add2(const uint4& q, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+    float2* v2 = reinterpret_cast<float2*>(v);
+#pragma unroll
+    for (int i = 0; i < 4; i++) v2[i] = __fadd2_rn(v2[i], __half22float2(h[i]));
+}
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     __half2 h = __floats2half2_rn(fminf(lo, 65504.0f), fminf(hi, 65504.0f));
     return *reinterpret_cast<uint32_t*>(&h);
@@ -274,13 +291,19 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
 #pragma unroll 1
             for (int layer = 0; layer < NET_LAYERS; layer++) {
                 const uint32_t lpar = (uint32_t)((iter * NET_LAYERS + layer) & 1);
+                const bool second = (layer & 1) != 0;          // conv2 of a block: add the skip connection
+                const bool last = (layer == NET_LAYERS - 1);
+                // skip connection (fp16 panels in L2): the first 8 of the 16 panels are fetched while the MMAs still
+                // run, the rest two chunk pairs ahead of their use (register budget: 672 threads x 96)
+                const uint4 zero4 = make_uint4(0, 0, 0, 0);
+                uint4 sk[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) sk[j] = (second && valid) ? rrow[(size_t)j * TC_M] : zero4;
                 mbar_wait(bar_accum + 8 * tile, lpar, 128);
                 if (nb_lo) mbar_wait(bar_accum + 8 * (tile - 1), lpar, 64);
                 if (nb_hi) mbar_wait(bar_accum + 8 * (tile + 1), lpar, 64);
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
-                const bool second = (layer & 1) != 0;          // conv2 of a block: add the skip connection
-                const bool last = (layer == NET_LAYERS - 1);
                 const float* bl = bias + layer * 128;
                 // 8 chunks of 16 accumulator columns, TMEM loads double-buffered against the math / stores
                 float va[16], vb[16];
@@ -288,38 +311,39 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
 #pragma unroll
                 for (int ch = 0; ch < 8; ch++) {
                     float* v = (ch & 1) ? vb : va;
-                    uint4 rx0 = make_uint4(0, 0, 0, 0), rx1 = make_uint4(0, 0, 0, 0);
-                    if (second && valid) {                       // skip connection (fp16 panels in L2)
-                        rx0 = rrow[(size_t)(2 * ch) * TC_M];
-                        rx1 = rrow[(size_t)(2 * ch + 1) * TC_M];
-                    }
                     tmem_ld_wait();
                     if (ch < 7) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
+                    float2* v2 = reinterpret_cast<float2*>(v);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 16) + j);
-                        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                        v2[2 * j] = __fadd2_rn(v2[2 * j], make_float2(b4.x, b4.y));
+                        v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(b4.z, b4.w));
                     }
-                    f16x8_add(rx0, v);
-                    f16x8_add(rx1, v + 8);
-#pragma unroll
-                    for (int j = 0; j < 16; j++) v[j] = valid ? fmaxf(v[j], 0.0f) : 0.0f;
+                    f16x8_add2(sk[(2 * ch) & 7], v);
+                    f16x8_add2(sk[(2 * ch + 1) & 7], v + 8);
+                    if (ch < 4 && second && valid) {             // refill the two registers just consumed: panels +8
+                        sk[(2 * ch) & 7] = rrow[(size_t)(2 * ch + 8) * TC_M];
+                        sk[(2 * ch + 1) & 7] = rrow[(size_t)(2 * ch + 9) * TC_M];
+                    }
                     if (last) {
                         if (valid) {
 #pragma unroll
                             for (int j = 0; j < 4; j++)
-                                reinterpret_cast<float4*>(arow + ch * 16)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                                reinterpret_cast<float4*>(arow + ch * 16)[j] =
+                                    make_float4(fmaxf(v[4 * j], 0.f), fmaxf(v[4 * j + 1], 0.f), fmaxf(v[4 * j + 2], 0.f), fmaxf(v[4 * j + 3], 0.f));
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 2; j++) {
-                            uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                                  pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                            const float* w8 = v + 8 * j;
+                            uint4 pk = valid ? make_uint4(relu_bf16x2(w8[0], w8[1]), relu_bf16x2(w8[2], w8[3]),
+                                                          relu_bf16x2(w8[4], w8[5]), relu_bf16x2(w8[6], w8[7]))
+                                             : zero4;                    // padding rows stay zero
                             *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * TC_PANEL_BYTES) = pk;
                             if (second && valid)
-                                rrow[(size_t)(ch * 2 + j) * TC_M] =
-                                    make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
-                                               pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
+                                rrow[(size_t)(ch * 2 + j) * TC_M] = make_uint4(relu_f16x2(w8[0], w8[1]), relu_f16x2(w8[2], w8[3]),
+                                                                               relu_f16x2(w8[4], w8[5]), relu_f16x2(w8[6], w8[7]));
                         }
                     }
                 }
