@@ -37,6 +37,9 @@ extern "C" {
 
 /* self-play flags */
 #define UTTT_SP_CORRECT_TERMINAL_SIGN 1 /* opt out of the reference's inverted terminal sign (cpp/uttt_mcts.cpp:19-21) */
+#define UTTT_SP_THROUGHPUT 2            /* standard AlphaZero search instead of the reference-exact one: evaluated root
+                                           with Dirichlet noise, virtual loss, `batch_size` = leaves per tree per round
+                                           (<= 16), single expansion per leaf, correct terminal sign (not in the reference) */
 
 typedef struct uttt_engine uttt_engine;
 
@@ -126,8 +129,11 @@ int uttt_net_forward(uttt_engine *e, const uint32_t *states_dev, int64_t n, int 
  * Synchronous.  roots/scores/counts/n_scores are HOST pointers.
  * scores[i][0..n_scores[i]) follow legal_actions(root i) order; counts are the raw visit counts. */
 int uttt_mcts_search(uttt_engine *e, const uint32_t *roots, int32_t n_roots, int32_t evaluate_count,
-                     int32_t batch_size, float temperature, int32_t evaluator, float *scores /* n*81 */,
-                     int32_t *counts /* n*81 */, int32_t *n_scores /* n */);
+                     int32_t batch_size, float temperature, int32_t evaluator, int32_t flags,
+                     float *scores /* n*81 */, int32_t *counts /* n*81 */, int32_t *n_scores /* n */);
+/* Dirichlet root noise of the throughput mode: p = (1-eps) p + eps * Dir(alpha); defaults alpha 0.3, eps 0.25
+ * (AlphaZero's settings; the reference has no noise).  eps = 0 disables it. */
+int uttt_set_root_noise(uttt_engine *e, float alpha, float eps);
 
 /* step-wise form for a caller-side evaluator (python_bindings.cpp:11-47 `wrap_python_inference`) */
 int uttt_mcts_begin(uttt_engine *e, const uint32_t *roots, int32_t n_roots, int32_t evaluate_count,

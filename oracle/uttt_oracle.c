@@ -529,3 +529,43 @@ int orc_selfplay_hash(uint32_t seed, uint64_t game, int sims, int batch, uint32_
     for (int i = 0; i < t; i++) { z[i] = (int8_t)value; value = -value; }
     return t;
 }
+
+/* ------------------------------------------------ throughput-mode cross-check (see uttt_oracle.h) */
+static void az_expand(orc_node *nd, const float *pol) {
+    int legal[81];
+    int nl = orc_legal_actions(&nd->state, legal);
+    float lp[81], sum = 0.0f;
+    for (int k = 0; k < nl; k++) { lp[k] = pol[legal[k]]; sum += lp[k]; }
+    for (int k = 0; k < nl; k++) lp[k] = (sum > 0) ? lp[k] / sum : 1.0f / (float)nl;
+    expand(nd, lp, nl);
+}
+
+int orc_az_search_hash(const orc_state *root_state, int sims, int *counts_out) {
+    int tmp[81];
+    if (orc_is_lose(root_state) || orc_legal_actions(root_state, tmp) == 0) return 0;
+    float pol[81], val;
+    orc_node *root = node_new(root_state, 0.0f);
+    orc_hash_eval(root_state, pol, &val);
+    az_expand(root, pol);                          /* evaluated root; its value is not backed up */
+    for (int i = 0; i < sims; i++) {
+        orc_node *path[ORC_MAX_PATH];
+        int plen = 0;
+        orc_node *nd = root;
+        float v;
+        for (;;) {
+            path[plen++] = nd;
+            if (orc_is_done(&nd->state)) { v = orc_is_lose(&nd->state) ? -1.0f : 0.0f; break; }
+            if (nd->n_child == 0) {
+                orc_hash_eval(&nd->state, pol, &v);
+                az_expand(nd, pol);
+                break;
+            }
+            nd = next_child_node(nd);              /* same PUCT arithmetic (C=1, first maximum) */
+        }
+        backpropagate(path, plen, v);
+    }
+    for (int k = 0; k < root->n_child; k++) counts_out[k] = root->child[k]->n;
+    int n = root->n_child;
+    node_free(root);
+    return n;
+}

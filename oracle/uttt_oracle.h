@@ -86,6 +86,12 @@ int  orc_selfplay_hash(uint32_t seed, uint64_t game, int sims, int batch,
                        uint32_t *states /* 81*8 */, uint16_t *counts /* 81*81 */,
                        uint8_t *actions /* 81 */, int8_t *z /* 81 */);
 
+/* ---- CPU cross-check of the CUDA library's THROUGHPUT search mode (csrc/tree_tp_kernels.cu) in its
+ * sequential configuration: one leaf per round, no root noise.  NOT a restatement of the reference (the
+ * reference has no such mode): plain PUCT with an evaluated root, single expansion per leaf,
+ * correct terminal sign, same fp32 operation order as the kernels.  Returns #root children. */
+int  orc_az_search_hash(const orc_state *root, int sims, int *counts_out /* 81 */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -67,6 +67,8 @@ def oracle():
                                   C.POINTER(C.c_int), u8p]
         L.orc_selfplay_hash.argtypes = [C.c_uint32, C.c_uint64, C.c_int, C.c_int, u32p, u16p, u8p, i8p]
         L.orc_selfplay_hash.restype = C.c_int
+        L.orc_az_search_hash.argtypes = [SP, C.c_int, i32p]
+        L.orc_az_search_hash.restype = C.c_int
         _oracle = L
     return _oracle
 
@@ -153,3 +155,10 @@ def ref_mcts(w, temperature, sims, batch):
     st = np.zeros(2, np.int32)
     n = ref().ref_mcts_scores_hash(np.ascontiguousarray(w, dtype=np.uint32), temperature, sims, batch, sc, st)
     return sc[:n].copy(), st
+
+
+def oracle_az_search(w, sims):
+    s = state_from_packed(w)
+    cn = np.zeros(81, np.int32)
+    n = oracle().orc_az_search_hash(C.byref(s), sims, cn)
+    return cn[:n].copy()

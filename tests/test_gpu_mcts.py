@@ -145,3 +145,52 @@ def test_boltzman_device(golden_dir):
         for T in (0.5, 2.0):
             out = np.array(uttt_cpp.boltzman(g["xs"][i].tolist(), T), np.float32)
             np.testing.assert_allclose(out, g["T%g" % T][i], rtol=2e-6, atol=1e-9)
+
+
+# ------------------------------------------------------------------ throughput mode (not in the reference)
+def test_throughput_search_sequential_matches_cpu_cross_check(eng):
+    """m = 1 leaf per round, no root noise: plain PUCT with an evaluated root -- bit-exact visit counts vs
+    oracle/uttt_oracle.c:orc_az_search_hash under the hash evaluator"""
+    import engine
+    eng.set_root_noise(0.3, 0.0)
+    sts = np.concatenate([O.playout_states(808, g)[0][::4] for g in range(24)])[:300]
+    for sims in (50, 200):
+        scores, counts, ns = eng.mcts_search(sts, sims, 1, 1.0, engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+        for i in range(0, len(sts), 5):
+            cn = O.oracle_az_search(sts[i], sims)
+            assert ns[i] == len(cn)
+            assert (counts[i, :ns[i]] == cn).all(), (sims, i)
+    eng.set_root_noise(0.3, 0.25)
+
+
+def test_throughput_search_invariants_with_virtual_loss_and_noise(eng):
+    import engine
+    sts = np.concatenate([O.playout_states(909, g)[0][:-1:5] for g in range(20)])[:200]
+    for m in (4, 8):
+        eng.set_root_noise(0.3, 0.25)
+        s1, c1, n1 = eng.mcts_search(sts, 200, m, 1.0, engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+        s2, c2, n2 = eng.mcts_search(sts, 200, m, 1.0, engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+        assert (c1 == c2).all()                                   # reproducible: depends only on (seed, m)
+        for i in range(len(sts)):
+            _, legal, _ = O.oracle_probe(sts[i])
+            assert n1[i] == len(legal)
+            assert c1[i, :n1[i]].sum() == 200 and (c1[i, n1[i]:] == 0).all()      # every simulation lands on a root child
+        eng.set_root_noise(0.3, 0.0)
+        s3, c3, n3 = eng.mcts_search(sts, 200, m, 1.0, engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+        assert (c3 != c1).any()                                   # the noise does change the search
+    eng.set_root_noise(0.3, 0.25)
+
+
+def test_throughput_selfplay_runs_and_is_reproducible():
+    import engine
+    e = engine.Engine(n_slots=64, max_sims=200, max_batch=8, max_games=96)
+    try:
+        h1 = e.selfplay(96, sims=200, batch=8, seed=5, evaluator=engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+        st, cn, z = h1.samples()
+        assert (h1.lens >= 17).all() and (cn.sum(1) == 200).all()
+        h2 = e.selfplay(96, sims=200, batch=8, seed=5, evaluator=engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+        assert (h1.actions == h2.actions).all() and (h1.counts == h2.counts).all() and (h1.lens == h2.lens).all()
+        h3 = e.selfplay(96, sims=200, batch=8, seed=6, evaluator=engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+        assert (h3.actions != h1.actions).any()
+    finally:
+        e.close()

@@ -41,7 +41,8 @@ constexpr int NET_ACTIONS = 81;   // DN_OUTPUT_SIZE      dual_network.py:15
 // ---------------------------------------------------------------- tree storage
 constexpr int PATH_CAP = 96;      // root + at most 81 plies
 
-enum : int32_t { PHASE_DONE = 0, PHASE_SEARCH = 1, PHASE_PENDING = 2 };
+enum : int32_t { PHASE_DONE = 0, PHASE_SEARCH = 1, PHASE_PENDING = 2, PHASE_ROOT = 3, PHASE_ROOT_PENDING = 4 };
+constexpr int TP_MAX_LEAVES = 16;   // throughput mode: leaves per tree per round
 enum : int32_t { MODE_SEARCH = 0, MODE_SELFPLAY = 1 };
 
 struct alignas(16) TreeCtl {
@@ -62,6 +63,10 @@ struct TreeParams {
     int32_t n_trees, node_cap, sims, batch, mode, flags;
     PackedState* root;        // [n_trees]
     PackedState* leaf_state;  // [n_trees]
+    // throughput mode (tree_tp_kernels.cu): per tree up to TP_MAX_LEAVES pending leaves
+    int32_t* tp_paths;        // [n_trees][TP_MAX_LEAVES][PATH_CAP]
+    int32_t* tp_aux;          // [n_trees][2][TP_MAX_LEAVES]: path lengths, evaluator rows
+    float dir_alpha, dir_eps; // Dirichlet root noise
     TreeCtl* ctl;             // [n_trees]
     int32_t* path;            // [n_trees][PATH_CAP]
     // nodes, [n_trees][node_cap], 16 B each: {n:16 | action<<16, w, p, first_child:20 | n_children<<20}
@@ -94,6 +99,8 @@ struct TreeParams {
 // kernels' host launchers (each returns cudaGetLastError of the launch)
 cudaError_t launch_tree_begin(const TreeParams& p, cudaStream_t s);
 cudaError_t launch_tree_round(const TreeParams& p, cudaStream_t s);
+cudaError_t launch_tree_tp_begin(const TreeParams& p, cudaStream_t s);
+cudaError_t launch_tree_tp_round(const TreeParams& p, cudaStream_t s);
 cudaError_t launch_hash_eval(const PackedState* states, const int32_t* k, const int32_t* count, int max_rows,
                              float* policy, float* value, int row_stride, int copy_stride, cudaStream_t s);
 cudaError_t launch_scores(const int32_t* counts, const int32_t* n, int n_trees, float temperature,

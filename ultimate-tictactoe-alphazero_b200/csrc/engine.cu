@@ -59,6 +59,7 @@ struct uttt_engine {
     uttt_config cfg;
     int n_sm;
     int node_cap;
+    int rows_per_slot;      // evaluator rows per slot (max_batch: throughput mode queues up to that many leaves)
     cudaStream_t stream;
     cudaStream_t lane_stream[N_LANES];
     cudaEvent_t ev_fork, ev_join[N_LANES];
@@ -106,13 +107,14 @@ struct EvalBufs {
 
 EvalBufs bufs_of(uttt_engine* e, size_t first_slot, int lane) {
     EvalBufs b;
-    b.nn_states = e->tp.nn_states + first_slot;
-    b.nn_k = e->tp.nn_k + first_slot;
-    b.nn_planes = e->tp.nn_planes + first_slot * 243;
+    size_t first_row = first_slot * (size_t)e->rows_per_slot;
+    b.nn_states = e->tp.nn_states + first_row;
+    b.nn_k = e->tp.nn_k + first_row;
+    b.nn_planes = e->tp.nn_planes + first_row * 243;
     b.policy = e->policy + first_slot * e->cfg.max_batch * 81;
     b.value = e->value + first_slot * e->cfg.max_batch;
-    b.act_a = e->act_a + first_slot * 81 * 128;
-    b.act_b = e->act_b + first_slot * 81 * 128;
+    b.act_a = e->act_a + first_row * 81 * 128;
+    b.act_b = e->act_b + first_row * 81 * 128;
     b.resid = e->tc_resid + (size_t)lane * e->n_sm * 512 * 64;     // fp16 panels: 128 KiB per CTA
     return b;
 }
@@ -191,19 +193,22 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     e->n_sm = prop.multiProcessorCount;
     // worst case per tree: root + 81 root children + (sum of k over evaluations <= sims) * 81
     e->node_cap = 1 + 81 + 81 * cfg->max_sims;
+    e->rows_per_slot = cfg->max_batch < TP_MAX_LEAVES ? cfg->max_batch : TP_MAX_LEAVES;
     UTTT_CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     size_t S = (size_t)cfg->n_slots, NC = (size_t)e->node_cap, G = (size_t)cfg->max_games;
+    size_t R = S * (size_t)e->rows_per_slot;      // evaluator row capacity
     TreeParams& t = e->tp;
     t.node_cap = e->node_cap;
-    if (ealloc(e, &t.root, S) || ealloc(e, &t.leaf_state, S) || ealloc(e, &t.ctl, S) ||
+    if (ealloc(e, &t.root, S) || ealloc(e, &t.leaf_state, S * TP_MAX_LEAVES) ||
+        ealloc(e, &t.tp_paths, S * TP_MAX_LEAVES * PATH_CAP) || ealloc(e, &t.tp_aux, S * 2 * TP_MAX_LEAVES) || ealloc(e, &t.ctl, S) ||
         ealloc(e, &t.path, S * PATH_CAP) || ealloc(e, &t.nodes, S * NC) ||
-        ealloc(e, &t.nn_states, S) || ealloc(e, &t.nn_planes, S * 243 + 8) || ealloc(e, &t.nn_tree, S) ||
-        ealloc(e, &t.nn_k, S) || ealloc(e, &t.nn_count, 2 * N_LANES) || ealloc(e, &t.out_counts, S * 81) ||
+        ealloc(e, &t.nn_states, R) || ealloc(e, &t.nn_planes, R * 243 + 8) || ealloc(e, &t.nn_tree, R) ||
+        ealloc(e, &t.nn_k, R) || ealloc(e, &t.nn_count, 2 * N_LANES) || ealloc(e, &t.out_counts, S * 81) ||
         ealloc(e, &t.out_n, S) || ealloc(e, &t.counters, 8) || ealloc(e, &t.hist_states, G * 81) ||
         ealloc(e, &t.hist_counts, G * 81 * 81) || ealloc(e, &t.hist_actions, G * 81) || ealloc(e, &t.hist_len, G) ||
         ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
-        ealloc(e, &e->act_a, S * 81 * 128) || ealloc(e, &e->act_b, S * 81 * 128) ||
+        ealloc(e, &e->act_a, R * 81 * 128) || ealloc(e, &e->act_b, R * 81 * 128) ||
         ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128)) {
         uttt_destroy(e);
         return 1;
@@ -220,6 +225,8 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     for (int i = 0; i < EV_POOL; i++) UTTT_CUDA_OK(cudaEventCreate(&e->ev[i]));
     t.policy = e->policy;
     t.value = e->value;
+    t.dir_alpha = 0.3f;
+    t.dir_eps = 0.25f;
     *out = e;
     return 0;
 }
@@ -427,33 +434,54 @@ int uttt_mcts_finish(uttt_engine* e, float temperature, float* scores, int32_t* 
 }
 
 int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int32_t sims, int32_t batch,
-                     float temperature, int32_t evaluator, float* scores, int32_t* counts, int32_t* n_scores) {
+                     float temperature, int32_t evaluator, int32_t flags, float* scores, int32_t* counts,
+                     int32_t* n_scores) {
     UTTT_CHECK(evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_FP32 || evaluator == UTTT_EVAL_HASH,
                "uttt_mcts_search needs a device evaluator; use the step-wise calls for UTTT_EVAL_HOST");
-    if (uttt_mcts_begin(e, roots, n_roots, sims, batch)) return 1;
+    const bool tp = (flags & UTTT_SP_THROUGHPUT) != 0;
+    UTTT_CHECK(!tp || batch <= TP_MAX_LEAVES, "throughput mode: at most %d leaves per tree per round", TP_MAX_LEAVES);
+    if (uttt_mcts_begin(e, roots, n_roots, sims, batch)) return 1;     // uploads roots, runs the compat begin kernel
     if (n_roots == 0) return 0;
     TreeParams& t = e->tp;
+    t.flags = flags;
+    if (tp) UTTT_CUDA_OK(launch_tree_tp_begin(t, e->stream));
     // rounds are enqueued without host synchronisation; the tree kernel ignores finished trees.
-    // Upper bound on rounds: every round retires >= 1 simulation of every unfinished tree.
-    int max_rounds = sims + 1;
+    // Upper bound on rounds: every round retires >= 1 simulation of every unfinished tree (+ root evaluation).
+    const int rows = tp ? n_roots * batch : n_roots;
+    int max_rounds = sims + 3;
     int r = 0;
     while (r < max_rounds) {
         int stop = (r + CHECK_EVERY < max_rounds) ? r + CHECK_EVERY : max_rounds;
         for (; r < stop; r++) {
             t.parity = r & 1;
-            UTTT_CUDA_OK(launch_tree_round(t, e->stream));
-            if (run_evaluator(e, bufs_of(e, 0, 0), evaluator, t.nn_count + t.parity, n_roots, e->stream, nullptr)) return 1;
+            UTTT_CUDA_OK(tp ? launch_tree_tp_round(t, e->stream) : launch_tree_round(t, e->stream));
+            if (run_evaluator(e, bufs_of(e, 0, 0), evaluator, t.nn_count + t.parity, rows, e->stream, nullptr)) return 1;
         }
         UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + ((r - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost,
                                      e->stream));
         UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
-        if (e->h_count[0] == 0) break;      // nothing was queued in the last round: every tree is done
+        if (e->h_count[0] == 0 && !tp) break;      // nothing was queued in the last round: every tree is done
+        if (tp) {                                   // throughput rounds may queue nothing (terminal-only rounds)
+            UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long),
+                                         cudaMemcpyDeviceToHost, e->stream));
+            UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+            if ((int64_t)e->h_counters[6] >= n_roots) break;
+            if (r >= max_rounds) max_rounds += CHECK_EVERY;      // terminal-only rounds are bounded per round
+            UTTT_CHECK(max_rounds < 64 * (sims + 3), "throughput search did not finish");
+        }
     }
     UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
     UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
     e->s_n_roots = n_roots;
     return uttt_mcts_finish(e, temperature, scores, counts, n_scores);
+}
+
+int uttt_set_root_noise(uttt_engine* e, float alpha, float eps) {
+    UTTT_CHECK(e && alpha > 0.0f && eps >= 0.0f && eps <= 1.0f, "bad root-noise parameters");
+    e->tp.dir_alpha = alpha;
+    e->tp.dir_eps = eps;
+    return 0;
 }
 
 int uttt_boltzman(const float* xs, int32_t n, float temperature, float* out) {
@@ -481,6 +509,9 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
                "self-play needs a device evaluator");
     int n_trees = (int)((n_games < e->cfg.n_slots) ? n_games : e->cfg.n_slots);
     if (check_search_args(e, n_trees, sims, batch)) return 1;
+    const bool tp = (flags & UTTT_SP_THROUGHPUT) != 0;
+    UTTT_CHECK(!tp || batch <= TP_MAX_LEAVES, "throughput mode: at most %d leaves per tree per round", TP_MAX_LEAVES);
+    const int rows_per_tree = tp ? batch : 1;
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
     for (int i = 0; i < 4; i++) { e->prof_ms[i] = 0.0; e->prof_launches[i] = 0; }
@@ -506,7 +537,10 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
         p.n_trees = lane_trees[l];
         p.root += first; p.leaf_state += first; p.ctl += first; p.path += first * PATH_CAP;
         p.nodes += first * (size_t)e->node_cap;
-        p.nn_states += first; p.nn_planes += first * 243; p.nn_tree += first; p.nn_k += first;
+        size_t first_row = first * (size_t)e->rows_per_slot;
+        p.leaf_state += first * (TP_MAX_LEAVES - 1);      // leaf_state is [slot][TP_MAX_LEAVES]
+        p.tp_paths += first * TP_MAX_LEAVES * PATH_CAP; p.tp_aux += first * 2 * TP_MAX_LEAVES;
+        p.nn_states += first_row; p.nn_planes += first_row * 243; p.nn_tree += first_row; p.nn_k += first_row;
         p.nn_count += 2 * l;
         p.policy = e->policy + first * e->cfg.max_batch * 81;
         p.value = e->value + first * e->cfg.max_batch;
@@ -520,12 +554,12 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     for (int l = 0; l < n_lanes; l++) {
         ls[l] = (n_lanes == 1) ? s : e->lane_stream[l];
         if (n_lanes > 1) UTTT_CUDA_OK(cudaStreamWaitEvent(ls[l], e->ev_fork, 0));
-        UTTT_CUDA_OK(launch_tree_begin(lane_tp[l], ls[l]));
+        UTTT_CUDA_OK(tp ? launch_tree_tp_begin(lane_tp[l], ls[l]) : launch_tree_begin(lane_tp[l], ls[l]));
         e->prof_launches[0] += 1;
     }
     // every round retires >= 1 simulation of every live slot: hard upper bound on rounds
     int64_t waves = (n_games + n_trees - 1) / n_trees;
-    int64_t max_rounds = waves * 82 * (int64_t)(sims + 1) + CHECK_EVERY;
+    int64_t max_rounds = waves * 82 * (int64_t)(sims + 3) * (tp ? 4 : 1) + CHECK_EVERY;
     int64_t r = 0;
     bool done = false;
     while (!done && r < max_rounds) {
@@ -535,9 +569,10 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
                 cudaEvent_t* ev = e->ev + 4 * (in_window * N_LANES + l);
                 lane_tp[l].parity = (int)(r & 1);
                 cudaEventRecord(ev[0], ls[l]);
-                UTTT_CUDA_OK(launch_tree_round(lane_tp[l], ls[l]));
+                UTTT_CUDA_OK(tp ? launch_tree_tp_round(lane_tp[l], ls[l]) : launch_tree_round(lane_tp[l], ls[l]));
                 e->prof_launches[0] += 1;
-                if (run_evaluator(e, lane_bufs[l], evaluator, lane_tp[l].nn_count + lane_tp[l].parity, lane_trees[l],
+                if (run_evaluator(e, lane_bufs[l], evaluator, lane_tp[l].nn_count + lane_tp[l].parity,
+                                  lane_trees[l] * rows_per_tree,
                                   ls[l], ev + 1))
                     return 1;
             }

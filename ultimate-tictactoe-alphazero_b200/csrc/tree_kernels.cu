@@ -25,44 +25,9 @@
 //
 // All float arithmetic on n/w/p uses explicit round-to-nearest intrinsics in the reference's
 // operation order (no FMA contraction, no reassociation): cpp/setup.py:10 builds with -O3 only.
-#include "common.cuh"
+#include "tree_common.cuh"
 
 namespace uttt {
-
-constexpr unsigned FULL = 0xFFFFFFFFu;
-constexpr int WARPS_PER_BLOCK = 4;
-
-struct TreeView {
-    uint4* node;     // [node_cap]
-    int32_t* path;   // [PATH_CAP]
-};
-
-__device__ __forceinline__ TreeView view_of(const TreeParams& P, int t) {
-    TreeView v = {P.nodes + (size_t)t * (size_t)P.node_cap, P.path + (size_t)t * PATH_CAP};
-    return v;
-}
-
-__device__ __forceinline__ uint4 make_node(int action, float p) {
-    return make_uint4((uint32_t)action << 16, 0u, __float_as_uint(p), 0u);
-}
-__device__ __forceinline__ int node_n(const uint4& q) { return (int)(q.x & 0xFFFFu); }
-__device__ __forceinline__ int node_action(const uint4& q) { return (int)(q.x >> 16); }
-__device__ __forceinline__ uint32_t node_base(const uint4& q) { return q.w & 0xFFFFFu; }
-__device__ __forceinline__ int node_cnt(const uint4& q) { return (int)(q.w >> 20); }
-
-__device__ __forceinline__ PackedState warp_load_state(const PackedState* p, int lane) {
-    uint32_t x = (lane < 8) ? reinterpret_cast<const uint32_t*>(p)[lane] : 0u;
-    PackedState s;
-#pragma unroll
-    for (int i = 0; i < 8; i++) s.w[i] = __shfl_sync(FULL, x, i);
-    return s;
-}
-__device__ __forceinline__ void warp_store_state(PackedState* p, const PackedState& s, int lane) {
-    uint32_t x = s.w[0];
-#pragma unroll
-    for (int i = 1; i < 8; i++) x = (lane == i) ? s.w[i] : x;
-    if (lane < 8) reinterpret_cast<uint32_t*>(p)[lane] = x;
-}
 
 // cpp/uttt_mcts.cpp:92-103: root expanded up-front with the uniform prior 1/L (never evaluated, Q-M1)
 __device__ void init_root(const TreeParams& P, const TreeView& T, TreeCtl& c, const PackedState& rs, int lane) {
@@ -145,33 +110,6 @@ __device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, i
     if (lane == 0) atomicAdd(P.counters + 3, (unsigned long long)k);
 }
 
-// Philox temperature-1 sampling over the root visit counts; returns the chosen action.
-__device__ int sample_move(const TreeParams& P, const TreeView& T, const TreeCtl& c, const uint32_t lm[3], int lane) {
-    int L = c.n_root;
-    int tot = 0;
-    for (int i = lane; i < L; i += 32) tot += node_n(T.node[1 + i]);
-    tot = __reduce_add_sync(FULL, tot);
-    Philox4 r = philox4x32(P.seed, 1u, (uint32_t)c.game, (uint32_t)(c.game >> 32), (uint32_t)c.ply, 0u);
-    uint32_t pick = __umulhi(r.x, (uint32_t)tot);
-    int carry = 0, chosen = -1;
-    for (int base = 0; base < L && chosen < 0; base += 32) {
-        int i = base + lane;
-        int v = (i < L) ? node_n(T.node[1 + i]) : 0;
-        int incl = v;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            int o = __shfl_up_sync(FULL, incl, off);
-            if (lane >= off) incl += o;
-        }
-        incl += carry;
-        unsigned hit = __ballot_sync(FULL, (i < L) && ((uint32_t)incl > pick));
-        if (hit) chosen = base + (__ffs((int)hit) - 1);
-        carry = __shfl_sync(FULL, incl, 31);
-    }
-    if (chosen < 0) chosen = 0;
-    return nth_legal(lm, chosen);
-}
-
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_begin_kernel(TreeParams P) {
     int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
@@ -228,7 +166,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
         if (c.sims_left <= 0) {
             // ---------------- the move is decided: root visit counts (cpp/uttt_mcts.cpp:177-180)
             if (P.mode == MODE_SEARCH) {
-                for (int i = lane; i < c.n_root; i += 32) P.out_counts[(size_t)t * 81 + i] = node_n(T.node[1 + i]);
+                for (int i = lane; i < 81; i += 32) P.out_counts[(size_t)t * 81 + i] = (i < c.n_root) ? node_n(T.node[1 + i]) : 0;
                 if (lane == 0) P.out_n[t] = c.n_root;
                 c.phase = PHASE_DONE;
                 break;
@@ -320,7 +258,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
             node = (int)cbase + besti;
             link = bestlink;
             PackedState nx;
-            next_state(st, (int)(bestx >> 16), nx);
+            next_state(st, (int)((bestx >> 16) & 0x7Fu), nx);
             st = nx;
             if (lane == 0) T.path[plen] = node;
             plen++;

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(HERE, "libuttt_b200.so")
 
 EVAL_NET_BF16, EVAL_NET_FP32, EVAL_HASH, EVAL_HOST = 0, 1, 2, 3
 SP_CORRECT_TERMINAL_SIGN = 1
+SP_THROUGHPUT = 2
 
 _vp = C.c_void_p
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -55,7 +56,9 @@ ABI = {
     "uttt_destroy": ([_vp], C.c_int),
     "uttt_upload_weights": ([_vp, C.POINTER(UtttWeights), C.c_int], C.c_int),
     "uttt_net_forward": ([_vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp], C.c_int),
-    "uttt_mcts_search": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _vp, _vp, _vp], C.c_int),
+    "uttt_mcts_search": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp],
+                         C.c_int),
+    "uttt_set_root_noise": ([_vp, C.c_float, C.c_float], C.c_int),
     "uttt_mcts_begin": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32], C.c_int),
     "uttt_mcts_advance": ([_vp, C.POINTER(C.c_int32)], C.c_int),
     "uttt_mcts_get_leaves": ([_vp, _vp, _vp, _vp], C.c_int),
@@ -284,13 +287,17 @@ class Engine:
         return pol, val
 
     # ---- search over many roots (host numpy in / out)
-    def mcts_search(self, roots, sims, batch, temperature, evaluator):
+    def set_root_noise(self, alpha=0.3, eps=0.25):
+        """Dirichlet root noise of the throughput mode (eps=0 disables)"""
+        _check(self.lib.uttt_set_root_noise(self.h, float(alpha), float(eps)))
+
+    def mcts_search(self, roots, sims, batch, temperature, evaluator, flags=0):
         roots = np.ascontiguousarray(roots, dtype=np.uint32).reshape(-1, 8)
         n = roots.shape[0]
         scores = np.zeros((n, 81), np.float32)
         counts = np.zeros((n, 81), np.int32)
         ns = np.zeros((n,), np.int32)
-        _check(self.lib.uttt_mcts_search(self.h, _ptr(roots), n, sims, batch, float(temperature), evaluator,
+        _check(self.lib.uttt_mcts_search(self.h, _ptr(roots), n, sims, batch, float(temperature), evaluator, flags,
                                          _ptr(scores), _ptr(counts), _ptr(ns)))
         return scores, counts, ns
 

@@ -34,6 +34,10 @@ SP_MAX_SLOTS = 4096           # concurrent games per GPU
 SP_SEED = None                # None: draw from np.random
 CORRECTED_LABELS = False      # True: label from the true winner instead of self_play_cpp.py:95-99
 CORRECTED_TERMINAL_SIGN = False
+SP_SEARCH_MODE = "compat"     # "compat": reference-exact search; "throughput": AlphaZero-standard search
+                              #   (evaluated root + Dirichlet noise, virtual loss, MCTS_BATCH_SIZE leaves / round)
+SP_DIRICHLET_ALPHA = 0.3      # throughput mode only
+SP_DIRICHLET_EPS = 0.25
 
 _engine = None
 last_stats = {}
@@ -103,6 +107,9 @@ def _run(model, n_games):
     seed = int(np.random.randint(0, 2 ** 31 - 1)) if SP_SEED is None else int(SP_SEED)
     ev = _eng.EVAL_NET_FP32 if SP_NUMERICS == "fp32" else _eng.EVAL_NET_BF16
     flags = _eng.SP_CORRECT_TERMINAL_SIGN if CORRECTED_TERMINAL_SIGN else 0
+    if SP_SEARCH_MODE == "throughput":
+        flags |= _eng.SP_THROUGHPUT
+        eng.set_root_noise(SP_DIRICHLET_ALPHA, SP_DIRICHLET_EPS)
     if SP_TEMPERATURE != 1.0:
         raise NotImplementedError("the on-device sampler implements SP_TEMPERATURE == 1.0 (the reference's setting)")
     hist = eng.selfplay(n_games, sims=PV_EVALUATE_COUNT, batch=MCTS_BATCH_SIZE, seed=seed, evaluator=ev, flags=flags)
