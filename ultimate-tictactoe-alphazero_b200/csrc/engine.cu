@@ -134,22 +134,18 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         UTTT_CUDA_OK(launch_trunk_fp32(e->w, b.nn_planes, count, max_rows, b.act_a, b.act_b, s));
         e->prof_launches[1] += 1 + 2 * NET_BLOCKS;
     } else if (evaluator == UTTT_EVAL_NET_BF16) {
-        // conv_input is accounted to the tree/gather share; the trunk events bracket trunk_tc_kernel alone
-        UTTT_CUDA_OK(launch_conv_input(e->w, b.nn_planes, count, max_rows, b.act_a, s));
-        e->prof_launches[0] += 1;
+        // conv_input runs inside the trunk kernels (tensor pipe, "layer -1").  Two trunk variants are enqueued; each
+        // reads the queue length on the device and exits at once if the batch is not in its range: small batches
+        // (one wave of CTA pairs) are latency-bound -> cluster variant, larger ones are throughput-bound -> one CTA
+        // per group with 4 accumulator tiles.  Counted as ONE trunk launch per round.
         if (ev3) cudaEventRecord(ev3[0], s);
-        // Two trunk variants are enqueued; each reads the queue length on the device and exits at once if the
-        // batch is not in its range: small batches (one wave of CTA pairs) are latency-bound -> cluster variant,
-        // larger ones are throughput-bound -> one CTA per group with 4 accumulator tiles.
         if (e->trunk_variant == 2) {
-            if (max_rows > trunk_tc2_capacity(e->n_sm)) {
-                UTTT_CUDA_OK(launch_trunk_tc(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
+            if (max_rows > trunk_tc2_capacity(e->n_sm))
+                UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
                                              trunk_tc2_capacity(e->n_sm)));
-                e->prof_launches[1] += 1;
-            }
-            UTTT_CUDA_OK(launch_trunk_tc2(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+            UTTT_CUDA_OK(launch_trunk_tc2(e->w, b.nn_planes, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
         } else {
-            UTTT_CUDA_OK(launch_trunk_tc(e->w, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+            UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
         }
         e->prof_launches[1] += 1;
     } else {
@@ -236,7 +232,7 @@ int uttt_destroy(uttt_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
-    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, e->w.pol_conv_w,
+    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b};
     for (float* p : wp) if (p) cudaFree(p);
@@ -332,6 +328,19 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
     for (int j = 0; j < 256; j++)
         for (int i = 0; i < 81; i++) v1_t[i * 256 + j] = v1w[j * 81 + i];
 
+    // conv_input for the tensor pipe: [12 tap slots (9 used)][2 panels][128 co][8 ci]; channels 3..15 are zero
+    {
+        std::vector<__nv_bfloat16> ci_h((size_t)12 * 2 * 128 * 8, __float2bfloat16(0.0f));
+        for (int tap = 0; tap < 9; tap++)
+            for (int ci = 0; ci < 3; ci++)
+                for (int co = 0; co < 128; co++)
+                    ci_h[((size_t)(tap * 2) * 128 + co) * 8 + ci] = __float2bfloat16(ci_w[(tap * 3 + ci) * 128 + co]);
+        if (!W.conv_in_w_bf16) UTTT_CUDA_OK(cudaMalloc((void**)&W.conv_in_w_bf16, ci_h.size() * sizeof(__nv_bfloat16)));
+        UTTT_CUDA_OK(cudaMemcpy(W.conv_in_w_bf16, ci_h.data(), ci_h.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        if (!W.bias_all) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_all, 33 * 128 * sizeof(float)));
+        UTTT_CUDA_OK(cudaMemcpy(W.bias_all, ci_b.data(), 128 * sizeof(float), cudaMemcpyHostToDevice));
+        UTTT_CUDA_OK(cudaMemcpyAsync(W.bias_all + 128, W.res_b, 32 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    }
     if (to_device(&W.conv_in_w, ci_w) || to_device(&W.conv_in_b, ci_b) || to_device(&W.pol_conv_w, pc_w) || to_device(&W.pol_conv_b, pc_b) ||
         to_device(&W.pol_fc_w, pf_t) || to_device(&W.pol_fc_b, pfb) || to_device(&W.val_conv_w, vc_w) ||
         to_device(&W.val_conv_b, vc_b) || to_device(&W.val_fc1_w, v1_t) || to_device(&W.val_fc1_b, v1b) ||

@@ -42,6 +42,9 @@ constexpr int TC_A_BYTES = 16 * TC_PANEL_BYTES;
 constexpr int TC_STAGE_BYTES = 16384;         // half a tap: 64 ci x 128 co bf16
 constexpr int TC_STAGES = 5;
 constexpr int TC_STAGES_PER_LAYER = 18;
+constexpr int TC_IN_STAGES = 3;                // conv_input: 9 taps x (K=16: 3 real channels) in 3 stages of 4 taps
+constexpr int TC_GROUP_STAGES = TC_IN_STAGES + NET_LAYERS * TC_STAGES_PER_LAYER;
+constexpr int TC_GROUP_LAYERS = NET_LAYERS + 1;  // conv_input runs as layer -1 through the same pipeline
 constexpr int TC_BAR_OFF = TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES;
 constexpr int TC_SMEM_BYTES = TC_BAR_OFF + 256;
 constexpr int TC_ISSUERS = 4;                  // one MMA-issuing warp per accumulator tile
@@ -186,7 +189,9 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
-                const float* __restrict__ bias,         // [32][128]
+                const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
+                const float* __restrict__ bias,         // [33][128]: conv_input shift, then the 32 trunk layers
+                const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
                 float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
                 float* resid,                           // [gridDim][16 panels][512 rows][8] fp16 skip connection (L2-resident)
                 const int32_t* __restrict__ count,
@@ -258,25 +263,18 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
             uint8_t* srow = sA + (size_t)(TC_LEAD + m) * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile * 128);
 
-            // prologue: conv_input output -> skip buffer (fp32) + bf16 A operand of layer 0
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ch++) {
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    float4 x = valid ? reinterpret_cast<const float4*>(arow + ch * 32)[j] : make_float4(0, 0, 0, 0);
-                    v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+            // prologue: the three input planes of this row go into channel panel 0 (channels 3..15 are zero): the
+            // A operand of conv_input, which runs as "layer -1" on the tensor pipe with K = 16 per tap
+            {
+                uint4 pk = make_uint4(0, 0, 0, 0);
+                if (valid) {
+                    const __nv_bfloat16* px = planes + (size_t)gpos * 243 + (size_t)(r * 9 + c);
+                    uint32_t x0 = (uint32_t)__bfloat16_as_ushort(px[0]), x1 = (uint32_t)__bfloat16_as_ushort(px[81]),
+                             x2 = (uint32_t)__bfloat16_as_ushort(px[162]);
+                    pk = make_uint4(x0 | (x1 << 16), x2, 0u, 0u);
                 }
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint4 pk = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                          pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-                    *reinterpret_cast<uint4*>(srow + (size_t)(ch * 4 + j) * TC_PANEL_BYTES) = pk;
-                    if (valid)
-                        rrow[(size_t)(ch * 4 + j) * TC_M] =
-                            make_uint4(pack_f16x2(v[8 * j], v[8 * j + 1]), pack_f16x2(v[8 * j + 2], v[8 * j + 3]),
-                                       pack_f16x2(v[8 * j + 4], v[8 * j + 5]), pack_f16x2(v[8 * j + 6], v[8 * j + 7]));
-                }
+                *reinterpret_cast<uint4*>(srow) = pk;
+                *reinterpret_cast<uint4*>(srow + TC_PANEL_BYTES) = make_uint4(0, 0, 0, 0);
             }
             const bool nb_lo = (quarter == 0) && (tile > 0);            // rows also read by tile-1's MMAs
             const bool nb_hi = (quarter == 3) && (tile < tiles - 1);    // rows also read by tile+1's MMAs
@@ -289,9 +287,10 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
             }
 
 #pragma unroll 1
-            for (int layer = 0; layer < NET_LAYERS; layer++) {
-                const uint32_t lpar = (uint32_t)((iter * NET_LAYERS + layer) & 1);
-                const bool second = (layer & 1) != 0;          // conv2 of a block: add the skip connection
+            for (int layer = -1; layer < NET_LAYERS; layer++) {
+                const uint32_t lpar = (uint32_t)((iter * TC_GROUP_LAYERS + layer + 1) & 1);
+                const bool second = (layer >= 0) && (layer & 1) != 0;   // conv2 of a block: add the skip connection
+                const bool keep = second || (layer < 0);                // output feeds the next block: keep it as skip
                 const bool last = (layer == NET_LAYERS - 1);
                 // skip connection (fp16 panels in L2): the first 8 of the 16 panels are fetched while the MMAs still
                 // run, the rest two chunk pairs ahead of their use (register budget: 672 threads x 96)
@@ -302,9 +301,9 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 mbar_wait(bar_accum + 8 * tile, lpar, 128);
                 if (nb_lo) mbar_wait(bar_accum + 8 * (tile - 1), lpar, 64);
                 if (nb_hi) mbar_wait(bar_accum + 8 * (tile + 1), lpar, 64);
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 2] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
-                const float* bl = bias + layer * 128;
+                const float* bl = bias + (layer + 1) * 128;
                 // 8 chunks of 16 accumulator columns, TMEM loads double-buffered against the math / stores
                 float va[16], vb[16];
                 tmem_ld16(taddr, va);
@@ -341,7 +340,7 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                                                           relu_bf16x2(w8[4], w8[5]), relu_bf16x2(w8[6], w8[7]))
                                              : zero4;                    // padding rows stay zero
                             *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * TC_PANEL_BYTES) = pk;
-                            if (second && valid)
+                            if (keep && valid)
                                 rrow[(size_t)(ch * 2 + j) * TC_M] = make_uint4(relu_f16x2(w8[0], w8[1]), relu_f16x2(w8[2], w8[3]),
                                                                                relu_f16x2(w8[4], w8[5]), relu_f16x2(w8[6], w8[7]));
                         }
@@ -357,21 +356,22 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                         if (nb_hi) mbar_arrive(bar_act + 8 * (tile + 1));
                     }
                 }
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 3] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 3] = clock64();
             }
             tc_fence_before();
         } else if (warp == 16) {
             // ================= weight producer =================
 #pragma unroll 1
-            for (int n = 0; n < NET_LAYERS * TC_STAGES_PER_LAYER; n++) {
-                const int gn = iter * NET_LAYERS * TC_STAGES_PER_LAYER + n;
+            for (int n = 0; n < TC_GROUP_STAGES; n++) {
+                const int gn = iter * TC_GROUP_STAGES + n;
                 const int stage = gn % TC_STAGES;
                 const uint32_t par = (uint32_t)((gn / TC_STAGES) & 1);
                 mbar_wait(bar_empty + 8 * stage, par ^ 1u);
                 if (lane == 0) {
                     mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
-                    bulk_g2s(sB_u + stage * TC_STAGE_BYTES, wq + (size_t)n * (TC_STAGE_BYTES / 2), TC_STAGE_BYTES,
-                             bar_full + 8 * stage);
+                    const __nv_bfloat16* src = (n < TC_IN_STAGES) ? wq_in + (size_t)n * (TC_STAGE_BYTES / 2)
+                                                                  : wq + (size_t)(n - TC_IN_STAGES) * (TC_STAGE_BYTES / 2);
+                    bulk_g2s(sB_u + stage * TC_STAGE_BYTES, src, TC_STAGE_BYTES, bar_full + 8 * stage);
                 }
                 __syncwarp();
             }
@@ -383,31 +383,46 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
             const uint32_t tmem_d = tmem_base + (uint32_t)(tile * 128);
             const uint32_t a_tile = sA_u + (uint32_t)(TC_LEAD + tile * 128) * 16u;
 #pragma unroll 1
-            for (int layer = 0; layer < NET_LAYERS; layer++) {
-                mbar_wait(bar_act + 8 * tile, (uint32_t)((iter * NET_LAYERS + layer) & 1), 32);
+            for (int layer = -1; layer < NET_LAYERS; layer++) {
+                mbar_wait(bar_act + 8 * tile, (uint32_t)((iter * TC_GROUP_LAYERS + layer + 1) & 1), 32);
                 tc_fence_after();
-                if (dbg && blockIdx.x == 0 && iter == 0 && tile == 0 && leader) dbg[layer * 4 + 0] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && tile == 0 && leader && layer >= 0) dbg[layer * 4 + 0] = clock64();
+                const int n_st = (layer < 0) ? TC_IN_STAGES : TC_STAGES_PER_LAYER;
+                const int st0 = iter * TC_GROUP_STAGES + ((layer < 0) ? 0 : TC_IN_STAGES + layer * TC_STAGES_PER_LAYER);
 #pragma unroll 1
-                for (int s = 0; s < TC_STAGES_PER_LAYER; s++) {
-                    const int gn = (iter * NET_LAYERS + layer) * TC_STAGES_PER_LAYER + s;
+                for (int s = 0; s < n_st; s++) {
+                    const int gn = st0 + s;
                     const int stage = gn % TC_STAGES;
                     const uint32_t par = (uint32_t)((gn / TC_STAGES) & 1);
                     mbar_wait(bar_full + 8 * stage, par);
                     tc_fence_after();
                     if (leader) {
-                        const int tap = s >> 1, half = s & 1;
-                        const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
-                        const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * TC_PANEL_BYTES;
                         const uint32_t b0 = sB_u + (uint32_t)stage * TC_STAGE_BYTES;
+                        if (layer < 0) {
+                            // conv_input: block j of stage s is tap 4s+j, K = 16 (channel panels 0,1)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * TC_PANEL_BYTES, TC_PANEL_BYTES, 128),
-                                      make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), TC_IDESC, (uint32_t)((s | ks) != 0));
+                            for (int j = 0; j < 4; j++) {
+                                const int tap = 4 * s + j;
+                                if (tap < 9) {
+                                    const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                                    umma_bf16(tmem_d, make_desc(a_tile + (uint32_t)(shift * 16), TC_PANEL_BYTES, 128),
+                                              make_desc(b0 + (uint32_t)j * 4096u, 2048, 128), TC_IDESC, (uint32_t)(tap != 0));
+                                }
+                            }
+                        } else {
+                            const int tap = s >> 1, half = s & 1;
+                            const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                            const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * TC_PANEL_BYTES;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ks++) {
+                                umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * TC_PANEL_BYTES, TC_PANEL_BYTES, 128),
+                                          make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), TC_IDESC, (uint32_t)((s | ks) != 0));
+                            }
                         }
                         umma_commit(bar_empty + 8 * stage);          // frees the weight stage when the MMAs retire
-                        if (s == TC_STAGES_PER_LAYER - 1) {
+                        if (s == n_st - 1) {
                             umma_commit(bar_accum + 8 * tile);       // this tile's accumulator is complete
-                            if (dbg && blockIdx.x == 0 && iter == 0 && tile == 0) dbg[layer * 4 + 1] = clock64();
+                            if (dbg && blockIdx.x == 0 && iter == 0 && tile == 0 && layer >= 0) dbg[layer * 4 + 1] = clock64();
                         }
                     }
                     __syncwarp();
@@ -429,11 +444,12 @@ cudaError_t trunk_tc_init() {
     return cudaFuncSetAttribute(trunk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
 
-cudaError_t launch_trunk_tc(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* resid,
-                            int n_sm, cudaStream_t s, long long* dbg, int min_count) {
+cudaError_t launch_trunk_tc(const NetWeights& w, const __nv_bfloat16* planes, float* act, const int32_t* count,
+                            int max_rows, float* resid, int n_sm, cudaStream_t s, long long* dbg, int min_count) {
     int grid = max_rows < n_sm ? max_rows : n_sm;
     if (grid < 1) grid = 1;
-    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.res_b, act, resid, count, min_count, dbg);
+    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, resid,
+                                                            count, min_count, dbg);
     return cudaGetLastError();
 }
 

@@ -36,6 +36,9 @@ constexpr int A_BYTES = 16 * PANEL_BYTES;       // 71,680
 constexpr int STAGE_BYTES = 16384;
 constexpr int STAGES = 8;
 constexpr int STAGES_PER_LAYER = 18;
+constexpr int IN_STAGES = 3;                    // conv_input: 9 taps x (K=16: 3 real channels) in 3 stages of 4 taps
+constexpr int GROUP_STAGES = IN_STAGES + NET_LAYERS * STAGES_PER_LAYER;
+constexpr int GROUP_LAYERS = NET_LAYERS + 1;     // conv_input runs as layer -1 through the same pipeline
 constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
 constexpr int SMEM_BYTES = BAR_OFF + 256;
 constexpr int EPI_WARPS = 8 * LOC_TILES;         // (tile, lane quarter, column half)
@@ -205,8 +208,10 @@ __device__ __forceinline__ void f16x8_add2(const uint4& q, float* v) {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
-                 const float* __restrict__ bias,         // [32][128]
-                 float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
+                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
+                 const float* __restrict__ bias,         // [33][128]: conv_input shift, then the 32 trunk layers
+                 const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
+                 float* act,                             // out: trunk output [rows][81][128] fp32
                  uint4* skip,                            // [gridDim][16 panels][256 rows] fp16x8 skip connection
                  const int32_t* __restrict__ count,
                  int max_count,                          // batches above this are left to trunk_tc_kernel
@@ -291,22 +296,19 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
             const uint32_t peer_act = map_to_rank(bar_act + 8 * ((rank == 0) ? 0 : (T0 - 1)), peer);
             const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
-            // prologue: conv_input output -> fp16 skip buffer + bf16 A operand of layer 0
-#pragma unroll 1
-            for (int ch = 0; ch < 4; ch++) {
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    float4 x = valid ? reinterpret_cast<const float4*>(arow + ch * 16)[j] : make_float4(0, 0, 0, 0);
-                    v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+            // prologue: the three input planes of this row go into channel panel 0 (channels 3..15 are zero): the
+            // A operand of conv_input, which runs as "layer -1" on the tensor pipe with K = 16 per tap
+            {
+                uint4 pk = zero4;
+                if (chalf == 0 && valid) {
+                    const __nv_bfloat16* px = planes + (size_t)gpos * 243 + (size_t)(r * 9 + c);
+                    uint32_t x0 = (uint32_t)__bfloat16_as_ushort(px[0]), x1 = (uint32_t)__bfloat16_as_ushort(px[81]),
+                             x2 = (uint32_t)__bfloat16_as_ushort(px[162]);
+                    pk = make_uint4(x0 | (x1 << 16), x2, 0u, 0u);
                 }
-#pragma unroll
-                for (int j = 0; j < 2; j++) {
-                    uint4 pk = pack8_bf16(v + 8 * j);
-                    *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = pk;
-                    if (mirror) st_cluster_v4(peer_srow + (uint32_t)(ch * 2 + j) * PANEL_BYTES, pk);
-                    if (valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = pack8_f16(v + 8 * j);
-                }
+                uint8_t* dst = sA + (size_t)chalf * PANEL_BYTES + (size_t)(LEAD + lr) * 16;
+                *reinterpret_cast<uint4*>(dst) = pk;
+                if (mirror) st_cluster_v4(map_to_rank(sA_u + (uint32_t)chalf * PANEL_BYTES + peer_row * 16u, peer), pk);
             }
             fence_async_all();
             __syncwarp();
@@ -318,9 +320,10 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
             }
 
 #pragma unroll 1
-            for (int layer = 0; layer < NET_LAYERS; layer++) {
-                const uint32_t lpar = (uint32_t)((iter * NET_LAYERS + layer) & 1);
-                const bool second = (layer & 1) != 0;
+            for (int layer = -1; layer < NET_LAYERS; layer++) {
+                const uint32_t lpar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
+                const bool second = (layer >= 0) && (layer & 1) != 0;   // conv2 of a block: add the skip connection
+                const bool keep = second || (layer < 0);                // output is the input of the next block: keep it as skip
                 const bool last = (layer == NET_LAYERS - 1);
                 // the skip connection (8 x 16 B per thread) is fetched from L2 while the MMAs still run
                 uint4 sk[8];
@@ -330,9 +333,9 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 if (nb_lo) mbar_wait(bar_accum + 8 * (lt - 1), lpar, 64);
                 if (nb_hi) mbar_wait(bar_accum + 8 * (lt + 1), lpar, 64);
                 if (bnd) mbar_wait<true>(bar_bnd, lpar, 64);     // the peer's boundary-tile MMAs have retired
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 2] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
-                const float* bl = bias + layer * 128 + chalf * 64;
+                const float* bl = bias + (layer + 1) * 128 + chalf * 64;
                 float va[16], vb[16];
                 tmem_ld16(taddr, va);
 #pragma unroll
@@ -362,7 +365,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                             uint4 pk = valid ? relu_pack8_bf16(v + 8 * j) : zero4;      // padding rows stay zero
                             *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = pk;
                             if (mirror) st_cluster_v4(peer_srow + (uint32_t)(ch * 2 + j) * PANEL_BYTES, pk);
-                            if (second && valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = relu_pack8_f16(v + 8 * j);
+                            if (keep && valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = relu_pack8_f16(v + 8 * j);
                         }
                     }
                 }
@@ -377,21 +380,23 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                         if (bnd) mbar_arrive_remote(peer_act);
                     }
                 }
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0) dbg[layer * 4 + 3] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 3] = clock64();
             }
             tc_fence_before();
         } else if (warp == EPI_WARPS) {
             // ================= weight producer =================
             if (tiles == 0) continue;
 #pragma unroll 1
-            for (int n = 0; n < NET_LAYERS * STAGES_PER_LAYER; n++) {
-                const int gn = iter * NET_LAYERS * STAGES_PER_LAYER + n;
+            for (int n = 0; n < GROUP_STAGES; n++) {
+                const int gn = iter * GROUP_STAGES + n;
                 const int stage = gn % STAGES;
                 const uint32_t par = (uint32_t)((gn / STAGES) & 1);
                 mbar_wait(bar_empty + 8 * stage, par ^ 1u);
                 if (lane == 0) {
                     mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-                    bulk_g2s(sB_u + stage * STAGE_BYTES, wq + (size_t)n * (STAGE_BYTES / 2), STAGE_BYTES, bar_full + 8 * stage);
+                    const __nv_bfloat16* src = (n < IN_STAGES) ? wq_in + (size_t)n * (STAGE_BYTES / 2)
+                                                               : wq + (size_t)(n - IN_STAGES) * (STAGE_BYTES / 2);
+                    bulk_g2s(sB_u + stage * STAGE_BYTES, src, STAGE_BYTES, bar_full + 8 * stage);
                 }
                 __syncwarp();
             }
@@ -404,34 +409,50 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
             const uint32_t a_tile = sA_u + (uint32_t)(LEAD + lt * 128) * 16u;
             const bool signal_peer = has_peer && (lt == bnd_tile);
 #pragma unroll 1
-            for (int layer = 0; layer < NET_LAYERS; layer++) {
-                if (signal_peer) mbar_wait<true>(bar_act + 8 * lt, (uint32_t)((iter * NET_LAYERS + layer) & 1), 32);
-                else mbar_wait(bar_act + 8 * lt, (uint32_t)((iter * NET_LAYERS + layer) & 1), 32);
+            for (int layer = -1; layer < NET_LAYERS; layer++) {
+                const uint32_t apar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
+                if (signal_peer) mbar_wait<true>(bar_act + 8 * lt, apar, 32);
+                else mbar_wait(bar_act + 8 * lt, apar, 32);
                 fence_async_all();
                 tc_fence_after();
-                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[layer * 4 + 0] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0) dbg[layer * 4 + 0] = clock64();
+                const int n_st = (layer < 0) ? IN_STAGES : STAGES_PER_LAYER;
+                const int st0 = iter * GROUP_STAGES + ((layer < 0) ? 0 : IN_STAGES + layer * STAGES_PER_LAYER);
 #pragma unroll 1
-                for (int s = 0; s < STAGES_PER_LAYER; s++) {
-                    const int gn = (iter * NET_LAYERS + layer) * STAGES_PER_LAYER + s;
+                for (int s = 0; s < n_st; s++) {
+                    const int gn = st0 + s;
                     const int stage = gn % STAGES;
                     const uint32_t par = (uint32_t)((gn / STAGES) & 1);
                     mbar_wait(bar_full + 8 * stage, par);
                     tc_fence_after();
                     if (leader) {
-                        const int tap = s >> 1, half = s & 1;
-                        const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
-                        const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * PANEL_BYTES;
                         const uint32_t b0 = sB_u + (uint32_t)stage * STAGE_BYTES;
+                        if (layer < 0) {
+                            // conv_input: block j of stage s is tap 4s+j, K = 16 (channel panels 0,1)
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * PANEL_BYTES, PANEL_BYTES, 128),
-                                      make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), IDESC, (uint32_t)((s | ks) != 0));
+                            for (int j = 0; j < 4; j++) {
+                                const int tap = 4 * s + j;
+                                if (tap < 9) {
+                                    const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                                    umma_bf16(tmem_d, make_desc(a_tile + (uint32_t)(shift * 16), PANEL_BYTES, 128),
+                                              make_desc(b0 + (uint32_t)j * 4096u, 2048, 128), IDESC, (uint32_t)(tap != 0));
+                                }
+                            }
+                        } else {
+                            const int tap = s >> 1, half = s & 1;
+                            const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
+                            const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * PANEL_BYTES;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ks++) {
+                                umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * PANEL_BYTES, PANEL_BYTES, 128),
+                                          make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), IDESC, (uint32_t)((s | ks) != 0));
+                            }
                         }
                         umma_commit(bar_empty + 8 * stage);
-                        if (s == STAGES_PER_LAYER - 1) {
+                        if (s == n_st - 1) {
                             umma_commit(bar_accum + 8 * lt);
                             if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
-                            if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0) dbg[layer * 4 + 1] = clock64();
+                            if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && layer >= 0) dbg[layer * 4 + 1] = clock64();
                         }
                     }
                     __syncwarp();
@@ -456,12 +477,13 @@ cudaError_t trunk_tc2_init() {
 
 int trunk_tc2_capacity(int n_sm) { return (n_sm / 2) * tc2::MAX_P; }
 
-cudaError_t launch_trunk_tc2(const NetWeights& w, float* act, const int32_t* count, int max_rows, float* skip, int n_sm,
-                             cudaStream_t s, long long* dbg) {
+cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* act, const int32_t* count,
+                             int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg) {
     int pairs = n_sm / 2;
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
     tc2::trunk_tc2_kernel<<<2 * pairs, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.res_b, act, reinterpret_cast<uint4*>(skip), count, trunk_tc2_capacity(n_sm), dbg);
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, reinterpret_cast<uint4*>(skip), count,
+        trunk_tc2_capacity(n_sm), dbg);
     return cudaGetLastError();
 }
 
