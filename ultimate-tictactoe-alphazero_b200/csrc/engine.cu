@@ -393,16 +393,21 @@ int uttt_mcts_advance(uttt_engine* e, int32_t* n_pending) {
     TreeParams& t = e->tp;
     if (e->s_n_roots == 0) { *n_pending = 0; return 0; }
     UTTT_CHECK(e->s_pending == 0 || e->s_have_results, "pending leaves have no results yet (uttt_mcts_put_results)");
-    t.parity = e->s_round & 1;
-    UTTT_CUDA_OK(launch_tree_round(t, e->stream));
-    UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + t.parity, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
-    UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                 e->stream));
-    UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
-    UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
+    // a round may queue nothing although trees are still searching (bounded terminal work per round): keep going
+    for (;;) {
+        t.parity = e->s_round & 1;
+        UTTT_CUDA_OK(launch_tree_round(t, e->stream));
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + t.parity, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                     e->stream));
+        UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+        UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
+        e->s_round++;
+        if (e->h_count[0] > 0 || (int64_t)e->h_counters[6] >= e->s_n_roots) break;
+        UTTT_CHECK(e->s_round < 64 * (e->s_sims + 3), "search did not finish");
+    }
     e->s_pending = e->h_count[0];
     e->s_have_results = 0;
-    e->s_round++;
     *n_pending = e->s_pending;
     return 0;
 }
@@ -469,15 +474,13 @@ int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int
         UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + ((r - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost,
                                      e->stream));
         UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
-        if (e->h_count[0] == 0 && !tp) break;      // nothing was queued in the last round: every tree is done
-        if (tp) {                                   // throughput rounds may queue nothing (terminal-only rounds)
-            UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long),
-                                         cudaMemcpyDeviceToHost, e->stream));
-            UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
-            if ((int64_t)e->h_counters[6] >= n_roots) break;
-            if (r >= max_rounds) max_rounds += CHECK_EVERY;      // terminal-only rounds are bounded per round
-            UTTT_CHECK(max_rounds < 64 * (sims + 3), "throughput search did not finish");
-        }
+        // rounds may queue nothing (bounded terminal work per round): finished trees are counted on the device
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                     e->stream));
+        UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+        if ((int64_t)e->h_counters[6] >= n_roots) break;
+        if (r >= max_rounds) max_rounds += CHECK_EVERY;
+        UTTT_CHECK(max_rounds < 64 * (sims + 3), "search did not finish");
     }
     UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, e->stream));
     UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));

@@ -29,6 +29,8 @@
 
 namespace uttt {
 
+constexpr int MAX_TERMINAL_PER_ROUND = 8;
+
 // cpp/uttt_mcts.cpp:92-103: root expanded up-front with the uniform prior 1/L (never evaluated, Q-M1)
 __device__ void init_root(const TreeParams& P, const TreeView& T, TreeCtl& c, const PackedState& rs, int lane) {
     uint32_t lm[3];
@@ -80,24 +82,28 @@ __device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, i
     size_t row = (size_t)c.nn_row * (size_t)P.row_stride;
     for (int cp = 0; cp < k; cp++) {
         const float* pol = P.policy + (row + (size_t)cp * P.copy_stride) * 81;
-        // serial fp32 sum over the legal actions in ascending id (:144-152)
+        // one coalesced read of the policy row (lane a holds actions a, a+32, a+64), then the reference's serial
+        // fp32 sum over the legal actions in ascending id (:144-152) with the addends fetched by shuffle
+        float p0 = __ldg(pol + lane), p1 = __ldg(pol + 32 + lane), p2 = (lane < 17) ? __ldg(pol + 64 + lane) : 0.0f;
         float sum = 0.0f;
 #pragma unroll
         for (int j = 0; j < 3; j++) {
             uint32_t m = lm[j];
             while (m) {
-                int b = __ffs((int)m) - 1;
+                int a = 27 * j + __ffs((int)m) - 1;
                 m &= m - 1u;
-                sum = __fadd_rn(sum, __ldg(pol + 27 * j + b));
+                float v0 = __shfl_sync(FULL, p0, a & 31), v1 = __shfl_sync(FULL, p1, a & 31), v2 = __shfl_sync(FULL, p2, a & 31);
+                sum = __fadd_rn(sum, a < 32 ? v0 : (a < 64 ? v1 : v2));
             }
         }
         float uni = (L > 0) ? __fdiv_rn(1.0f, (float)L) : 0.0f;
         int reps = (P.copy_stride == 0) ? k : 1;       // identical rows: write all k copies at once
-        for (int a = lane; a < 81; a += 32) {
+        for (int q = 0, a = lane; a < 81; a += 32, q++) {
             if (legal_bit(lm, a)) {
-                float pr = (sum > 0.0f) ? __fdiv_rn(__ldg(pol + a), sum) : uni;     // :155-163
+                float pa = (q == 0) ? p0 : (q == 1 ? p1 : p2);
+                float pr = (sum > 0.0f) ? __fdiv_rn(pa, sum) : uni;                 // :155-163
                 int r = legal_rank(lm, a);
-                for (int q = 0; q < reps; q++) T.node[base + (cp + q) * L + r] = make_node(a, pr);
+                for (int c2 = 0; c2 < reps; c2++) T.node[base + (cp + c2) * L + r] = make_node(a, pr);
             }
         }
         if (P.copy_stride == 0) break;
@@ -138,7 +144,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_begin_kernel(TreePa
     init_root(P, T, c, rs, lane);
     if (c.n_root == 0) {                     // cpp/uttt_mcts.cpp:96-98: no legal move -> empty result
         c.phase = PHASE_DONE;
-        if (lane == 0) P.out_n[t] = 0;
+        if (lane == 0) { P.out_n[t] = 0; atomicAdd(P.counters + 6, 1ull); }
     } else {
         c.phase = PHASE_SEARCH;
     }
@@ -162,12 +168,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
     }
 
     PackedState root = warp_load_state(P.root + t, lane);
+    int n_terminal = 0;
     for (;;) {
         if (c.sims_left <= 0) {
             // ---------------- the move is decided: root visit counts (cpp/uttt_mcts.cpp:177-180)
             if (P.mode == MODE_SEARCH) {
                 for (int i = lane; i < 81; i += 32) P.out_counts[(size_t)t * 81 + i] = (i < c.n_root) ? node_n(T.node[1 + i]) : 0;
-                if (lane == 0) P.out_n[t] = c.n_root;
+                if (lane == 0) { P.out_n[t] = c.n_root; atomicAdd(P.counters + 6, 1ull); }
                 c.phase = PHASE_DONE;
                 break;
             }
@@ -272,6 +279,9 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
             backup(T, plen, 1, nullptr, 0, v, lane);
             c.sims_left -= 1;
             if (lane == 0) atomicAdd(P.counters + 3, 1ull);
+            // Every tree of the batch waits for the slowest warp of the round: bound the work of one round.  The
+            // remaining simulations simply continue next round (same order, same results).
+            if (++n_terminal >= MAX_TERMINAL_PER_ROUND && c.sims_left > 0) { c.phase = PHASE_SEARCH; break; }
             continue;
         }
 
