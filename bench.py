@@ -154,6 +154,8 @@ def main():
     ap.add_argument("--ref-moves", type=int, default=24, help="plies per step of the reference arm")
     ap.add_argument("--cpu-baseline-moves", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--saturated-games", type=int, default=4096,
+                    help="also time one cycle of this many concurrent games per GPU (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -237,6 +239,29 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---------------- secondary: the machine-filling workload (C5's per-GPU share: 4096 concurrent games)
+    sat = None
+    if args.saturated_games > 0:
+        eng.close()
+        eng = engine.Engine(n_slots=min(args.saturated_games, 4096), max_sims=args.sims, max_batch=args.batch,
+                            max_games=args.saturated_games, device=local_rank)
+        eng.upload_state_dict(sd_host)
+        eng.selfplay_device(args.saturated_games, sims=args.sims, batch=args.batch, seed=7, evaluator=ev_kind,
+                            game0=5 * 10 ** 6, stream=stream)                       # warm-up
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        st = eng.selfplay_device(args.saturated_games, sims=args.sims, batch=args.batch, seed=8, evaluator=ev_kind,
+                                 game0=6 * 10 ** 6 + rank * args.saturated_games, stream=stream)
+        e1.record(stream)
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        sat = {"games_per_gpu": args.saturated_games, "moves_per_s_rank0": int(st[0]) / (ms / 1e3),
+               "nn_evals_per_s_rank0": int(st[2]) / (ms / 1e3),
+               "trunk_tflops_equiv_rank0": int(st[2]) * TRUNK_FLOP_PER_POSITION / (ms / 1e3) / 1e12,
+               "note": "whole-pipeline rate (tree + trunk + heads, two overlapped lanes); trunk_tflops_equiv = evals x "
+                       "764.4 MFLOP / wall, i.e. a lower bound on the trunk kernels' own rate"}
+
     red = torch.tensor([dev_ms, e2e_s, wall_s], dtype=torch.float64, device=dev)
     tot = torch.tensor([plies, sims, evals, e2e_plies, all_launches], dtype=torch.float64, device=dev)
     if world > 1:
@@ -263,7 +288,9 @@ def main():
             "e2e": {"value": e2e_plies_all / e2e_s_max, "unit": "moves/s", "h2d_bytes_per_step": int(w_bytes),
                     "d2h_bytes_per_step": int(hist.nbytes)},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "tensor", "kernel": "trunk_tc_kernel" if args.numerics == "bf16" else "conv3x3_fp32_kernel",
+            "roofline": {"bound": "tensor",
+                         "kernel": "trunk_tc2_kernel / trunk_tc_kernel (one per round, chosen on the device by batch size)"
+                         if args.numerics == "bf16" else "conv3x3_fp32_kernel",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
                          "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
@@ -272,6 +299,7 @@ def main():
             "breakdown_ms_rank0": {"tree_kernels": tree_ms, "trunk": trunk_ms, "heads": heads_ms, "device_total": dev_ms,
                                    "rounds": rounds, "evals": evals, "plies": plies},
             "wall_s": wall_max,
+            "saturated": sat,
         }
         if world == 1 and not args.no_cpu_baseline:
             try:

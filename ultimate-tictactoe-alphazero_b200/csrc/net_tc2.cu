@@ -329,10 +329,10 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 uint4 sk[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) sk[j] = (second && valid) ? srow_skip[(size_t)j * SKIP_ROWS] : zero4;
-                mbar_wait(bar_accum + 8 * lt, lpar, 128);
-                if (nb_lo) mbar_wait(bar_accum + 8 * (lt - 1), lpar, 64);
-                if (nb_hi) mbar_wait(bar_accum + 8 * (lt + 1), lpar, 64);
-                if (bnd) mbar_wait<true>(bar_bnd, lpar, 64);     // the peer's boundary-tile MMAs have retired
+                mbar_wait(bar_accum + 8 * lt, lpar, 32);
+                if (nb_lo) mbar_wait(bar_accum + 8 * (lt - 1), lpar, 32);
+                if (nb_hi) mbar_wait(bar_accum + 8 * (lt + 1), lpar, 32);
+                if (bnd) mbar_wait<true>(bar_bnd, lpar, 32);     // the peer's boundary-tile MMAs have retired
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
                 const float* bl = bias + (layer + 1) * 128 + chalf * 64;
@@ -411,8 +411,8 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
 #pragma unroll 1
             for (int layer = -1; layer < NET_LAYERS; layer++) {
                 const uint32_t apar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
-                if (signal_peer) mbar_wait<true>(bar_act + 8 * lt, apar, 32);
-                else mbar_wait(bar_act + 8 * lt, apar, 32);
+                if (signal_peer) mbar_wait<true>(bar_act + 8 * lt, apar, 0);
+                else mbar_wait(bar_act + 8 * lt, apar, 0);
                 fence_async_all();
                 tc_fence_after();
                 if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0) dbg[layer * 4 + 0] = clock64();
