@@ -49,8 +49,8 @@ def launches():
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, "%s_launches.md" % tag), "w") as f:
         f.write("# ncu launch list, round %s\n\n" % tag)
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 1000 -c 600 python tools/prof_selfplay.py --games 500`\n")
-        f.write("(C3 workload: 500 games, 50 sims/move, batch 8; launches 1000..1599 of one self-play cycle; per-launch\n"
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 600 python tools/prof_selfplay.py --games 500`\n")
+        f.write("(C3 workload: 500 games, 50 sims/move, batch 8; launches 600..1199 of one self-play cycle; per-launch\n"
                 "times are cold-cache and serialised -- compare SHARES, not absolutes)\n\n")
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -67,7 +67,8 @@ def full(name):
     hdr, units = rows[0], rows[1]
     with open(os.path.join(P, "%s_%s_full.md" % (tag, name)), "w") as f:
         f.write("# ncu --set full, %s kernel, round %s\n\n" % (name, tag))
-        f.write("`ncu --set full --clock-control none --import-source on -k regex:%s -s 150 -c 2 python tools/prof_selfplay.py --games 500`\n\n" % name)
+        f.write("`ncu --set full --clock-control none --import-source on -k regex:<kernel> ...` on tools/trunk_timeline.py "
+                "(trunk: steady batch) / tools/prof_selfplay.py --games 500 (tree)\n\n")
         for r in rows[2:]:
             f.write("## launch id %s: %s grid %s block %s\n\n| metric | unit | value |\n|---|---|---:|\n" % (
                 r[0], r[hdr.index("Kernel Name")].split("(")[0], r[hdr.index("Grid Size")], r[hdr.index("Block Size")]))
@@ -79,5 +80,6 @@ def full(name):
 
 
 launches()
-full("trunk")
+full("trunk1")     # trunk_tc_kernel  (one CTA per group; batch of 740 positions)
+full("trunk2")     # trunk_tc2_kernel (CTA pair per group; batch of 345 positions)
 full("tree")
