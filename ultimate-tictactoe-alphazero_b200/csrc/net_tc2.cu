@@ -27,24 +27,31 @@ namespace uttt {
 namespace tc2 {
 
 constexpr int POS_ROWS = 100;
-constexpr int MAX_P = 5;
-constexpr int LOC_TILES = 2;                    // accumulator tiles per CTA
 constexpr int LEAD = 11;
-constexpr int AROWS = 280;                      // >= LEAD + 256 + 11
-constexpr int PANEL_BYTES = AROWS * 16;
-constexpr int A_BYTES = 16 * PANEL_BYTES;       // 71,680
 constexpr int STAGE_BYTES = 16384;
-constexpr int STAGES = 8;
 constexpr int STAGES_PER_LAYER = 18;
 constexpr int IN_STAGES = 3;                    // conv_input: 9 taps x (K=16: 3 real channels) in 3 stages of 4 taps
 constexpr int GROUP_STAGES = IN_STAGES + NET_LAYERS * STAGES_PER_LAYER;
 constexpr int GROUP_LAYERS = NET_LAYERS + 1;     // conv_input runs as layer -1 through the same pipeline
-constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
-constexpr int SMEM_BYTES = BAR_OFF + 256;
-constexpr int EPI_WARPS = 8 * LOC_TILES;         // (tile, lane quarter, column half)
-constexpr int THREADS = (EPI_WARPS + 1 + LOC_TILES) * 32;      // 608
-constexpr int SKIP_ROWS = 128 * LOC_TILES;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// LT = accumulator tiles per CTA.  LT=2: up to 5 positions per CTA pair (2+2 tiles), 8 weight stages.
+//                                   LT=3: up to 7 positions per CTA pair (3+3 tiles), 6 weight stages.
+template <int LT>
+struct Cfg {
+    static constexpr int LOC_TILES = LT;
+    static constexpr int MAX_P = (LT == 2) ? 5 : 7;
+    static constexpr int AROWS = (LEAD + 128 * LT + 11 + 7) / 8 * 8;
+    static constexpr int PANEL_BYTES = AROWS * 16;
+    static constexpr int A_BYTES = 16 * PANEL_BYTES;
+    static constexpr int STAGES = (LT == 2) ? 8 : 6;
+    static constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
+    static constexpr int SMEM_BYTES = BAR_OFF + 256;
+    static constexpr int EPI_WARPS = 8 * LT;         // (tile, lane quarter, column half)
+    static constexpr int THREADS = (EPI_WARPS + 1 + LT) * 32;
+    static constexpr int SKIP_ROWS = 128 * LT;
+    static constexpr uint32_t TMEM_COLS = (LT == 2) ? 256u : 512u;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -206,7 +213,8 @@ __device__ __forceinline__ void f16x8_add2(const uint4& q, float* v) {
     for (int i = 0; i < 4; i++) v2[i] = __fadd2_rn(v2[i], __half22float2(h[i]));
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
+template <int LT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<LT>::THREADS, 1)
 trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
                  const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
                  const float* __restrict__ bias,         // [33][128]: conv_input shift, then the 32 trunk layers
@@ -214,16 +222,22 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                  float* act,                             // out: trunk output [rows][81][128] fp32
                  uint4* skip,                            // [gridDim][16 panels][256 rows] fp16x8 skip connection
                  const int32_t* __restrict__ count,
-                 int max_count,                          // batches above this are left to trunk_tc_kernel
+                 int min_count, int max_count,           // this launch handles min_count < batch <= max_count
                  long long* dbg) {
+    using C = Cfg<LT>;
+    constexpr int LOC_TILES = C::LOC_TILES, MAX_P = C::MAX_P, PANEL_BYTES = C::PANEL_BYTES, A_BYTES = C::A_BYTES,
+                  STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS,
+                  SKIP_ROWS = C::SKIP_ROWS;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
     const int n_pos = *count;
-    if (n_pos > max_count) return;
+    if (n_pos <= min_count || n_pos > max_count) return;
     int P = (n_pos + n_pairs - 1) / n_pairs;
-    P = P < 1 ? 1 : (P >= 4 ? MAX_P : P);
+    P = P < 1 ? 1 : (P > MAX_P ? MAX_P : P);
+    if (P == 4) P = 5;                                // 4 positions need the same 4 tiles as 5
+    if (P == 6) P = 7;                                // 6 positions need 5 tiles = 3+2: same time as 3+3
     const int T = (P * POS_ROWS + 127) / 128;         // tiles of the pair: 1..4
     const int T0 = (T + 1) >> 1;                      // rank 0 takes the first ceil(T/2) tiles
     const int tiles = (rank == 0) ? T0 : T - T0;      // this CTA's tiles (0..2)
@@ -236,10 +250,10 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
     const uint32_t sA_u = smem_u32(sA);
     const uint32_t sB_u = sA_u + A_BYTES;
     const uint32_t bar_u = sA_u + BAR_OFF;
-    // barriers: full[8] @0, empty[8] @64, accum[2] @128, act[2] @144, bnd_accum @160; tmem holder @168
-    const uint32_t bar_full = bar_u, bar_empty = bar_u + 64, bar_accum = bar_u + 128, bar_act = bar_u + 144,
-                   bar_bnd = bar_u + 160;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 168);
+    // barriers: full[STAGES], empty[STAGES], accum[LT], act[LT], bnd_accum; then the tmem base holder
+    const uint32_t bar_full = bar_u, bar_empty = bar_u + 8 * STAGES, bar_accum = bar_u + 16 * STAGES,
+                   bar_act = bar_accum + 8 * LOC_TILES, bar_bnd = bar_act + 8 * LOC_TILES;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * STAGES + 16 * LOC_TILES + 8);
     // the tile of this CTA that touches the peer's rows, and the quarter-warp that owns the shared rows
     const int bnd_tile = (rank == 0) ? tiles - 1 : 0;
     const int bnd_quarter = (rank == 0) ? 3 : 0;
@@ -256,7 +270,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
     }
     if (warp == EPI_WARPS + 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                     "r"(256u)
+                     "r"(C::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -326,9 +340,12 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 const bool keep = second || (layer < 0);                // output is the input of the next block: keep it as skip
                 const bool last = (layer == NET_LAYERS - 1);
                 // the skip connection (8 x 16 B per thread) is fetched from L2 while the MMAs still run
-                uint4 sk[8];
+                // (LT = 3 runs 896 threads at 72 registers: only the first half is prefetched there, the second half is
+                // fetched two chunks ahead of its use)
+                constexpr int SKP = (LT == 2) ? 8 : 4;
+                uint4 sk[SKP];
 #pragma unroll
-                for (int j = 0; j < 8; j++) sk[j] = (second && valid) ? srow_skip[(size_t)j * SKIP_ROWS] : zero4;
+                for (int j = 0; j < SKP; j++) sk[j] = (second && valid) ? srow_skip[(size_t)j * SKIP_ROWS] : zero4;
                 mbar_wait(bar_accum + 8 * lt, lpar, 32);
                 if (nb_lo) mbar_wait(bar_accum + 8 * (lt - 1), lpar, 32);
                 if (nb_hi) mbar_wait(bar_accum + 8 * (lt + 1), lpar, 32);
@@ -350,8 +367,12 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                         v2[2 * j] = __fadd2_rn(v2[2 * j], make_float2(b4.x, b4.y));
                         v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(b4.z, b4.w));
                     }
-                    f16x8_add2(sk[2 * ch], v);
-                    f16x8_add2(sk[2 * ch + 1], v + 8);
+                    f16x8_add2(sk[(2 * ch) % SKP], v);
+                    f16x8_add2(sk[(2 * ch + 1) % SKP], v + 8);
+                    if (SKP == 4 && ch < 2 && second && valid) {     // refill the two registers just consumed: panels +4
+                        sk[(2 * ch) % SKP] = srow_skip[(size_t)(2 * ch + 4) * SKIP_ROWS];
+                        sk[(2 * ch + 1) % SKP] = srow_skip[(size_t)(2 * ch + 5) * SKIP_ROWS];
+                    }
                     if (last) {
                         if (valid) {
 #pragma unroll
@@ -465,25 +486,37 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
     __syncthreads();
     cluster_sync_all();                 // nobody exits while the peer may still write its margins / barriers
     if (warp == EPI_WARPS + 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
 }
 
 }  // namespace tc2
 
 cudaError_t trunk_tc2_init() {
-    return cudaFuncSetAttribute(tc2::trunk_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(tc2::trunk_tc2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         tc2::Cfg<2>::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(tc2::trunk_tc2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                tc2::Cfg<3>::SMEM_BYTES);
 }
 
-int trunk_tc2_capacity(int n_sm) { return (n_sm / 2) * tc2::MAX_P; }
+// largest batch the CTA-pair variants evaluate in one wave (7 positions per pair)
+int trunk_tc2_capacity(int n_sm) { return (n_sm / 2) * tc2::Cfg<3>::MAX_P; }
 
+// Two instantiations are enqueued; the queue length read on the device selects one:
+//   batch <= 5 * pairs : 2 accumulator tiles per CTA (lowest latency, 8-stage weight ring)
+//   batch <= 7 * pairs : 3 accumulator tiles per CTA
 cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* act, const int32_t* count,
                              int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg) {
     int pairs = n_sm / 2;
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
-    tc2::trunk_tc2_kernel<<<2 * pairs, tc2::THREADS, tc2::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, reinterpret_cast<uint4*>(skip), count,
-        trunk_tc2_capacity(n_sm), dbg);
+    const int cap2 = (n_sm / 2) * tc2::Cfg<2>::MAX_P, cap3 = (n_sm / 2) * tc2::Cfg<3>::MAX_P;
+    tc2::trunk_tc2_kernel<2><<<2 * pairs, tc2::Cfg<2>::THREADS, tc2::Cfg<2>::SMEM_BYTES, s>>>(
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, reinterpret_cast<uint4*>(skip), count, 0, cap2, dbg);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || max_rows <= cap2) return e;
+    tc2::trunk_tc2_kernel<3><<<2 * pairs, tc2::Cfg<3>::THREADS, tc2::Cfg<3>::SMEM_BYTES, s>>>(
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, reinterpret_cast<uint4*>(skip), count, cap2, cap3, dbg);
     return cudaGetLastError();
 }
 
