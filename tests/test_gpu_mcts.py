@@ -194,3 +194,42 @@ def test_throughput_selfplay_runs_and_is_reproducible():
         assert (h3.actions != h1.actions).any()
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------ edge cases
+def test_empty_and_finished_inputs(eng, golden_dir):
+    import engine
+    # no roots
+    s, c, n = eng.mcts_search(np.zeros((0, 8), np.uint32), 50, 8, 1.0, engine.EVAL_HASH)
+    assert s.shape == (0, 81) and n.shape == (0,)
+    # finished positions give an empty score vector (cpp/uttt_mcts.cpp:96-98), mixed with live ones
+    finals = np.stack([O.playout_states(11, g)[0][-1] for g in range(6)])
+    live = O.playout_states(11, 0)[0][3:5]
+    roots = np.concatenate([finals[:3], live, finals[3:]])
+    s, c, n = eng.mcts_search(roots, 50, 8, 1.0, engine.EVAL_HASH)
+    assert (n[:3] == 0).all() and (n[5:] == 0).all() and (n[3:5] > 0).all()
+    for i in (3, 4):
+        sc, cn, _ = O.oracle_mcts(roots[i], 1.0, 50, 8)
+        assert (s[i, :n[i]].view(np.uint32) == sc.view(np.uint32)).all()
+    s2, c2, n2 = eng.mcts_search(roots, 50, 4, 1.0, engine.EVAL_HASH, flags=engine.SP_THROUGHPUT)
+    assert (n2 == n).all()
+    # zero games
+    h = eng.selfplay(0, sims=50, batch=8, seed=1, evaluator=engine.EVAL_HASH)
+    assert h.stats[0] == 0
+    # argument validation surfaces as errors, not crashes
+    with pytest.raises(RuntimeError):
+        eng.mcts_search(live, 5000, 8, 1.0, engine.EVAL_HASH)          # > max_sims
+    with pytest.raises(RuntimeError):
+        eng.mcts_search(live, 50, 64, 1.0, engine.EVAL_HASH)           # > max_batch
+    with pytest.raises(RuntimeError):
+        eng.selfplay(10 ** 6, sims=50, batch=8, seed=1, evaluator=engine.EVAL_HASH, history=engine.History(1))
+
+
+def test_largest_configuration_800_sims_matches_oracle(eng):
+    """800 simulations / batch 8 (BASELINE config 4's search depth) on a handful of positions"""
+    import engine
+    sts = O.playout_states(2024, 3)[0][2:30:6]
+    scores, counts, ns = eng.mcts_search(sts, 800, 8, 1.0, engine.EVAL_HASH)
+    for i in range(len(sts)):
+        sc, cn, st = O.oracle_mcts(sts[i], 1.0, 800, 8)
+        assert (counts[i, :ns[i]] == cn).all() and (scores[i, :ns[i]].view(np.uint32) == sc.view(np.uint32)).all()
