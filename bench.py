@@ -292,7 +292,11 @@ def main():
                          "kernel": "trunk_tc2_kernel / trunk_tc_kernel (one per round, chosen on the device by batch size)"
                          if args.numerics == "bf16" else "conv3x3_fp32_kernel",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of trunk_tc2_kernel at a
+                         # batch of 345 positions (profiles/r1_trunk2_full.md): weights 9.4 MB + planes + head features
+                         "traffic": 13.03e6 if args.numerics == "bf16" else None,
+                         "traffic_unit": "bytes per launch (tensor-bound kernel: informational)",
                          "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                          "flop_per_launch": evals * TRUNK_FLOP_PER_POSITION / max(trunk_launches, 1),
                          "avg_launch_ms": trunk_ms / max(trunk_launches, 1), "launches": trunk_launches},

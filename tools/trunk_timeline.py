@@ -23,3 +23,4 @@ print("per layer (cycles): MMA issue span mean %.0f | issue->accum ready %.0f | 
     mma.mean(), wait_acc.mean(), epi[:-1].mean(), layer.mean()))
 print("even layers epi %.0f odd layers epi %.0f" % (epi[0:-1:2].mean(), epi[1:-1:2].mean()))
 print("first 4 layers:", (tl[:4] - tl[0, 0]).tolist())
+print("last 2 layers:", (tl[30:] - tl[30, 0]).tolist(), "last-layer epilogue", int(epi[-1]))

@@ -118,6 +118,7 @@ struct NetWeights {
     __nv_bfloat16* res_w_bf16;
     __nv_bfloat16* conv_in_w_bf16;   // conv_input as a K=16-per-tap tensor-core layer: [12 taps (9 used)][2][128][8]
     float* bias_all;                 // [33][128]: conv_input shift followed by the 32 trunk layers' shifts
+    float* head_w;                   // [3][128] policy conv (2 rows) + value conv, BN scale folded; [384..386] BN shifts
     // heads (fp32): policy conv [2][128] + shift[2], fc [81][162] + b; value conv [128] + shift, fc1 [256][81]+b, fc2 [256]+b
     float* pol_conv_w; float* pol_conv_b; float* pol_fc_w; float* pol_fc_b;
     float* val_conv_w; float* val_conv_b; float* val_fc1_w; float* val_fc1_b; float* val_fc2_w; float* val_fc2_b;
@@ -129,15 +130,18 @@ cudaError_t launch_conv_input(const NetWeights& w, const __nv_bfloat16* planes, 
                               float* out, cudaStream_t s);
 cudaError_t launch_trunk_fp32(const NetWeights& w, const __nv_bfloat16* planes, const int32_t* count, int max_rows,
                               float* act_a, float* act_b, cudaStream_t s);
-// planes: network input [rows][3][81] bf16; act: trunk output fp32 [rows][81][128]; resid: per-CTA fp16 skip panels
-cudaError_t launch_trunk_tc(const NetWeights& w, const __nv_bfloat16* planes, float* act, const int32_t* count,
+// planes: network input [rows][3][81] bf16; headfeat: [rows][243] output of the heads' 1x1 convs (computed in the
+// trunk's last epilogue); resid: per-CTA fp16 skip panels
+cudaError_t launch_trunk_tc(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
                             int max_rows, float* resid, int n_sm, cudaStream_t s, long long* dbg = nullptr,
                             int min_count = 0);
+cudaError_t launch_heads_fc(const NetWeights& w, const float* headfeat, const int32_t* count, int max_rows, float* policy,
+                            float* value, int row_stride, cudaStream_t s);
 cudaError_t launch_heads(const NetWeights& w, const float* act_f32, const __nv_bfloat16* act_bf16,
                          const int32_t* count, int max_rows, float* policy, float* value, int row_stride,
                          cudaStream_t s);
 // cluster-of-2 variant (net_tc2.cu): one group of positions per CTA pair; skip: [n_sm][16][256] fp16x8
-cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* act, const int32_t* count,
+cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
                              int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg = nullptr);
 cudaError_t trunk_tc2_init();
 int trunk_tc2_capacity(int n_sm);    // largest batch the cluster variant evaluates in one wave

@@ -69,6 +69,7 @@ struct uttt_engine {
     float* scores;          // [n_slots][81]
     float* act_a;           // [n_slots][81][128] fp32
     float* act_b;
+    float* headfeat;        // [rows][243] head 1x1-conv outputs written by the tensor-core trunk
     float* tc_resid;        // [n_sm][32][512][4] fp32 residual stream of the tensor-core trunk (per CTA)
     int32_t* fwd_count;     // device int for uttt_net_forward
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0 (diagnostics)
@@ -102,7 +103,7 @@ struct EvalBufs {
     const PackedState* nn_states;
     const int32_t* nn_k;
     const __nv_bfloat16* nn_planes;
-    float *policy, *value, *act_a, *act_b, *resid;
+    float *policy, *value, *act_a, *act_b, *resid, *headfeat;
 };
 
 EvalBufs bufs_of(uttt_engine* e, size_t first_slot, int lane) {
@@ -115,6 +116,7 @@ EvalBufs bufs_of(uttt_engine* e, size_t first_slot, int lane) {
     b.value = e->value + first_slot * e->cfg.max_batch;
     b.act_a = e->act_a + first_row * 81 * 128;
     b.act_b = e->act_b + first_row * 81 * 128;
+    b.headfeat = e->headfeat + first_row * 243;
     b.resid = e->tc_resid + (size_t)lane * e->n_sm * 512 * 64;     // fp16 panels: 128 KiB per CTA
     return b;
 }
@@ -141,18 +143,21 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         if (ev3) cudaEventRecord(ev3[0], s);
         if (e->trunk_variant == 2) {
             if (max_rows > trunk_tc2_capacity(e->n_sm))
-                UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
+                UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
                                              trunk_tc2_capacity(e->n_sm)));
-            UTTT_CUDA_OK(launch_trunk_tc2(e->w, b.nn_planes, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+            UTTT_CUDA_OK(launch_trunk_tc2(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
         } else {
-            UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.act_a, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+            UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
         }
         e->prof_launches[1] += 1;
     } else {
         UTTT_CHECK(false, "evaluator %d cannot run on the device", evaluator);
     }
     if (ev3) cudaEventRecord(ev3[1], s);
-    UTTT_CUDA_OK(launch_heads(e->w, b.act_a, nullptr, count, max_rows, b.policy, b.value, 1, s));
+    if (evaluator == UTTT_EVAL_NET_BF16)
+        UTTT_CUDA_OK(launch_heads_fc(e->w, b.headfeat, count, max_rows, b.policy, b.value, 1, s));
+    else
+        UTTT_CUDA_OK(launch_heads(e->w, b.act_a, nullptr, count, max_rows, b.policy, b.value, 1, s));
     e->prof_launches[2] += 1;
     if (ev3) cudaEventRecord(ev3[2], s);
     return 0;
@@ -204,7 +209,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         ealloc(e, &t.hist_counts, G * 81 * 81) || ealloc(e, &t.hist_actions, G * 81) || ealloc(e, &t.hist_len, G) ||
         ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
-        ealloc(e, &e->act_a, R * 81 * 128) || ealloc(e, &e->act_b, R * 81 * 128) ||
+        ealloc(e, &e->headfeat, R * 243) || ealloc(e, &e->act_a, R * 81 * 128) || ealloc(e, &e->act_b, R * 81 * 128) ||
         ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128)) {
         uttt_destroy(e);
         return 1;
@@ -232,7 +237,7 @@ int uttt_destroy(uttt_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
-    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, e->w.pol_conv_w,
+    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, e->w.head_w, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b};
     for (float* p : wp) if (p) cudaFree(p);
@@ -340,6 +345,13 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
         if (!W.bias_all) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_all, 33 * 128 * sizeof(float)));
         UTTT_CUDA_OK(cudaMemcpy(W.bias_all, ci_b.data(), 128 * sizeof(float), cudaMemcpyHostToDevice));
         UTTT_CUDA_OK(cudaMemcpyAsync(W.bias_all + 128, W.res_b, 32 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+    }
+    {
+        std::vector<float> hw(387);
+        for (int i = 0; i < 256; i++) hw[i] = pc_w[i];
+        for (int i = 0; i < 128; i++) hw[256 + i] = vc_w[i];
+        hw[384] = pc_b[0]; hw[385] = pc_b[1]; hw[386] = vc_b[0];
+        if (to_device(&W.head_w, hw)) return 1;
     }
     if (to_device(&W.conv_in_w, ci_w) || to_device(&W.conv_in_b, ci_b) || to_device(&W.pol_conv_w, pc_w) || to_device(&W.pol_conv_b, pc_b) ||
         to_device(&W.pol_fc_w, pf_t) || to_device(&W.pol_fc_b, pfb) || to_device(&W.val_conv_w, vc_w) ||

@@ -27,6 +27,8 @@
 // 64 cycles because every issue costs ~80 cycles of descriptor/uniform-register traffic); warp 17 owns TMEM.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace uttt {
@@ -192,7 +194,8 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
                 const float* __restrict__ bias,         // [33][128]: conv_input shift, then the 32 trunk layers
                 const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
-                float* act,                             // in: conv_input output, out: trunk output; [rows][81][128]
+                const float* __restrict__ headw,        // [3][128] head 1x1 convs (BN scale folded) + [384..386] shifts
+                float* headfeat,                        // out: [rows][243] = relu(policy conv)[2][81], relu(value conv)[81]
                 float* resid,                           // [gridDim][16 panels][512 rows][8] fp16 skip connection (L2-resident)
                 const int32_t* __restrict__ count,
                 int min_count,                          // batches up to this size are handled by trunk_tc2_kernel
@@ -258,7 +261,7 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
             const int r = idx / 10, c = idx - 10 * r;
             const int gpos = g * P + pos;
             const bool valid = (pos < P) && (r < 9) && (c < 9) && (gpos < n_pos);
-            float* arow = act + ((size_t)gpos * 81 + (size_t)(r * 9 + c)) * 128;
+            float* hrow = headfeat + (size_t)gpos * 243 + (size_t)(r * 9 + c);
             uint4* rrow = reinterpret_cast<uint4*>(resid) + (size_t)blockIdx.x * (16 * TC_M) + (size_t)m;
             uint8_t* srow = sA + (size_t)(TC_LEAD + m) * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(tile * 128);
@@ -286,12 +289,14 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 if (nb_hi) mbar_arrive(bar_act + 8 * (tile + 1));
             }
 
-#pragma unroll 1
-            for (int layer = -1; layer < NET_LAYERS; layer++) {
+            // the last layer (heads' 1x1 convs instead of a write-back) is a separate instantiation of the body so that
+            // its extra live registers do not burden the 32 common layers
+            int layer = -1;
+            auto epilogue_layer = [&](auto last_tag) {
+                constexpr bool last = decltype(last_tag)::value;
                 const uint32_t lpar = (uint32_t)((iter * TC_GROUP_LAYERS + layer + 1) & 1);
                 const bool second = (layer >= 0) && (layer & 1) != 0;   // conv2 of a block: add the skip connection
                 const bool keep = second || (layer < 0);                // output feeds the next block: keep it as skip
-                const bool last = (layer == NET_LAYERS - 1);
                 // skip connection (fp16 panels in L2): the first 8 of the 16 panels are fetched while the MMAs still
                 // run, the rest two chunk pairs ahead of their use (register budget: 672 threads x 96)
                 const uint4 zero4 = make_uint4(0, 0, 0, 0);
@@ -306,6 +311,7 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 const float* bl = bias + (layer + 1) * 128;
                 // 8 chunks of 16 accumulator columns, TMEM loads double-buffered against the math / stores
                 float va[16], vb[16];
+                float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
                 tmem_ld16(taddr, va);
 #pragma unroll
                 for (int ch = 0; ch < 8; ch++) {
@@ -325,12 +331,15 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                         sk[(2 * ch) & 7] = rrow[(size_t)(2 * ch + 8) * TC_M];
                         sk[(2 * ch + 1) & 7] = rrow[(size_t)(2 * ch + 9) * TC_M];
                     }
-                    if (last) {
-                        if (valid) {
+                    if constexpr (last) {
+                        // policy_conv / value_conv (1x1, dual_network.py:102,111): three dot products over this row
+                        const float* hw = headw + ch * 16;
 #pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                reinterpret_cast<float4*>(arow + ch * 16)[j] =
-                                    make_float4(fmaxf(v[4 * j], 0.f), fmaxf(v[4 * j + 1], 0.f), fmaxf(v[4 * j + 2], 0.f), fmaxf(v[4 * j + 3], 0.f));
+                        for (int j = 0; j < 16; j++) {
+                            float x = fmaxf(v[j], 0.0f);
+                            h0 = fmaf(x, __ldg(hw + j), h0);
+                            h1 = fmaf(x, __ldg(hw + 128 + j), h1);
+                            h2 = fmaf(x, __ldg(hw + 256 + j), h2);
                         }
                     } else {
 #pragma unroll
@@ -346,7 +355,7 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                         }
                     }
                 }
-                if (!last) {
+                if constexpr (!last) {
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
@@ -355,9 +364,16 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                         if (nb_lo) mbar_arrive(bar_act + 8 * (tile - 1));
                         if (nb_hi) mbar_arrive(bar_act + 8 * (tile + 1));
                     }
+                } else if (valid) {
+                    hrow[0] = fmaxf(h0 + __ldg(headw + 384), 0.0f);
+                    hrow[81] = fmaxf(h1 + __ldg(headw + 385), 0.0f);
+                    hrow[162] = fmaxf(h2 + __ldg(headw + 386), 0.0f);
                 }
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 3] = clock64();
-            }
+            };
+#pragma unroll 1
+            for (layer = -1; layer < NET_LAYERS - 1; layer++) epilogue_layer(std::false_type{});
+            epilogue_layer(std::true_type{});          // layer == NET_LAYERS - 1
             tc_fence_before();
         } else if (warp == 16) {
             // ================= weight producer =================
@@ -444,11 +460,11 @@ cudaError_t trunk_tc_init() {
     return cudaFuncSetAttribute(trunk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
 }
 
-cudaError_t launch_trunk_tc(const NetWeights& w, const __nv_bfloat16* planes, float* act, const int32_t* count,
+cudaError_t launch_trunk_tc(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
                             int max_rows, float* resid, int n_sm, cudaStream_t s, long long* dbg, int min_count) {
     int grid = max_rows < n_sm ? max_rows : n_sm;
     if (grid < 1) grid = 1;
-    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, resid,
+    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, w.head_w, headfeat, resid,
                                                             count, min_count, dbg);
     return cudaGetLastError();
 }

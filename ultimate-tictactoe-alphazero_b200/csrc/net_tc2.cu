@@ -21,6 +21,8 @@
 // instruction-latency bound, so it wants warps, not wider threads), 16 weight producer, 17-18 MMA issuers.
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace uttt {
@@ -46,7 +48,8 @@ struct Cfg {
     static constexpr int A_BYTES = 16 * PANEL_BYTES;
     static constexpr int STAGES = (LT == 2) ? 8 : 6;
     static constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
-    static constexpr int SMEM_BYTES = BAR_OFF + 256;
+    static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [128*LT rows][4] floats: head partial sums
+    static constexpr int SMEM_BYTES = HEAD_OFF + 128 * LT * 16;
     static constexpr int EPI_WARPS = 8 * LT;         // (tile, lane quarter, column half)
     static constexpr int THREADS = (EPI_WARPS + 1 + LT) * 32;
     static constexpr int SKIP_ROWS = 128 * LT;
@@ -219,7 +222,8 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                  const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
                  const float* __restrict__ bias,         // [33][128]: conv_input shift, then the 32 trunk layers
                  const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
-                 float* act,                             // out: trunk output [rows][81][128] fp32
+                 const float* __restrict__ headw,        // [3][128] policy conv (2) + value conv, BN scale folded; [384..386] shifts
+                 float* headfeat,                        // out: [rows][243] = relu(policy conv)[2][81], relu(value conv)[81]
                  uint4* skip,                            // [gridDim][16 panels][256 rows] fp16x8 skip connection
                  const int32_t* __restrict__ count,
                  int min_count, int max_count,           // this launch handles min_count < batch <= max_count
@@ -295,7 +299,8 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
             const int r = idx / 10, c = idx - 10 * r;
             const int gpos = g * P + pos;
             const bool valid = (pos < P) && (r < 9) && (c < 9) && (gpos < n_pos);
-            float* arow = act + ((size_t)gpos * 81 + (size_t)(r * 9 + c)) * 128 + chalf * 64;
+            float* hrow = headfeat + (size_t)gpos * 243 + (size_t)(r * 9 + c);
+            float4* hscr = reinterpret_cast<float4*>(smem + C::HEAD_OFF) + lr;
             uint4* srow_skip = skip + (size_t)blockIdx.x * (16 * SKIP_ROWS) + (size_t)(chalf * 8) * SKIP_ROWS + (size_t)lr;
             uint8_t* srow = sA + (size_t)(chalf * 8) * PANEL_BYTES + (size_t)(LEAD + lr) * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lt * 128 + chalf * 64);
@@ -333,12 +338,14 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 if (bnd) mbar_arrive_remote(peer_act);
             }
 
-#pragma unroll 1
-            for (int layer = -1; layer < NET_LAYERS; layer++) {
+            // the last layer (heads' 1x1 convs instead of a write-back) is a separate instantiation of the body so that
+            // its extra live registers do not burden the 32 common layers
+            int layer = -1;
+            auto epilogue_layer = [&](auto last_tag) {
+                constexpr bool last = decltype(last_tag)::value;
                 const uint32_t lpar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
                 const bool second = (layer >= 0) && (layer & 1) != 0;   // conv2 of a block: add the skip connection
                 const bool keep = second || (layer < 0);                // output is the input of the next block: keep it as skip
-                const bool last = (layer == NET_LAYERS - 1);
                 // the skip connection (8 x 16 B per thread) is fetched from L2 while the MMAs still run
                 // (LT = 3 runs 896 threads at 72 registers: only the first half is prefetched there, the second half is
                 // fetched two chunks ahead of its use)
@@ -354,6 +361,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 tc_fence_after();
                 const float* bl = bias + (layer + 1) * 128 + chalf * 64;
                 float va[16], vb[16];
+                float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
                 tmem_ld16(taddr, va);
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
@@ -373,12 +381,16 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                         sk[(2 * ch) % SKP] = srow_skip[(size_t)(2 * ch + 4) * SKIP_ROWS];
                         sk[(2 * ch + 1) % SKP] = srow_skip[(size_t)(2 * ch + 5) * SKIP_ROWS];
                     }
-                    if (last) {
-                        if (valid) {
+                    if constexpr (last) {
+                        // the trunk output never leaves the SM: policy_conv / value_conv (1x1, dual_network.py:102,111)
+                        // are three dot products over the channels this thread holds
+                        const float* hw = headw + chalf * 64 + ch * 16;
 #pragma unroll
-                            for (int j = 0; j < 4; j++)
-                                reinterpret_cast<float4*>(arow + ch * 16)[j] =
-                                    make_float4(fmaxf(v[4 * j], 0.f), fmaxf(v[4 * j + 1], 0.f), fmaxf(v[4 * j + 2], 0.f), fmaxf(v[4 * j + 3], 0.f));
+                        for (int j = 0; j < 16; j++) {
+                            float x = fmaxf(v[j], 0.0f);
+                            h0 = fmaf(x, __ldg(hw + j), h0);
+                            h1 = fmaf(x, __ldg(hw + 128 + j), h1);
+                            h2 = fmaf(x, __ldg(hw + 256 + j), h2);
                         }
                     } else {
 #pragma unroll
@@ -390,7 +402,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                         }
                     }
                 }
-                if (!last) {
+                if constexpr (!last) {
                     fence_async_all();
                     tc_fence_before();
                     __syncwarp();
@@ -400,9 +412,22 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                         if (nb_hi) mbar_arrive(bar_act + 8 * (lt + 1));
                         if (bnd) mbar_arrive_remote(peer_act);
                     }
+                } else {
+                    // combine the two column halves of the row (two warps) and emit BN shift + ReLU of the head convs
+                    if (chalf == 1) *hscr = make_float4(h0, h1, h2, 0.0f);
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + lt * 4 + quarter) : "memory");
+                    if (chalf == 0 && valid) {
+                        float4 o = *hscr;
+                        hrow[0] = fmaxf(h0 + o.x + __ldg(headw + 384), 0.0f);
+                        hrow[81] = fmaxf(h1 + o.y + __ldg(headw + 385), 0.0f);
+                        hrow[162] = fmaxf(h2 + o.z + __ldg(headw + 386), 0.0f);
+                    }
                 }
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 3] = clock64();
-            }
+            };
+#pragma unroll 1
+            for (layer = -1; layer < NET_LAYERS - 1; layer++) epilogue_layer(std::false_type{});
+            epilogue_layer(std::true_type{});          // layer == NET_LAYERS - 1
             tc_fence_before();
         } else if (warp == EPI_WARPS) {
             // ================= weight producer =================
@@ -506,17 +531,19 @@ int trunk_tc2_capacity(int n_sm) { return (n_sm / 2) * tc2::Cfg<3>::MAX_P; }
 // Two instantiations are enqueued; the queue length read on the device selects one:
 //   batch <= 5 * pairs : 2 accumulator tiles per CTA (lowest latency, 8-stage weight ring)
 //   batch <= 7 * pairs : 3 accumulator tiles per CTA
-cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* act, const int32_t* count,
+cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
                              int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg) {
     int pairs = n_sm / 2;
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
     const int cap2 = (n_sm / 2) * tc2::Cfg<2>::MAX_P, cap3 = (n_sm / 2) * tc2::Cfg<3>::MAX_P;
     tc2::trunk_tc2_kernel<2><<<2 * pairs, tc2::Cfg<2>::THREADS, tc2::Cfg<2>::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, reinterpret_cast<uint4*>(skip), count, 0, cap2, dbg);
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, 0,
+        cap2, dbg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || max_rows <= cap2) return e;
     tc2::trunk_tc2_kernel<3><<<2 * pairs, tc2::Cfg<3>::THREADS, tc2::Cfg<3>::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, act, reinterpret_cast<uint4*>(skip), count, cap2, cap3, dbg);
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, cap2,
+        cap3, dbg);
     return cudaGetLastError();
 }
 
