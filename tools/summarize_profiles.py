@@ -49,8 +49,8 @@ def launches():
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, "%s_launches.md" % tag), "w") as f:
         f.write("# ncu launch list, round %s\n\n" % tag)
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 600 python tools/prof_selfplay.py --games 500`\n")
-        f.write("(C3 workload: 500 games, 50 sims/move, batch 8; launches 600..1199 of one self-play cycle; per-launch\n"
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 1000 python tools/prof_selfplay.py --games 500`\n")
+        f.write("(C3 workload: 500 games, 50 sims/move, batch 8; launches 500..1499 of one self-play cycle; per-launch\n"
                 "times are cold-cache and serialised -- compare SHARES, not absolutes)\n\n")
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -80,6 +80,7 @@ def full(name):
 
 
 launches()
-full("trunk1")     # trunk_tc_kernel  (one CTA per group; batch of 740 positions)
-full("trunk2")     # trunk_tc2_kernel (CTA pair per group; batch of 345 positions)
+full("trunk1")     # trunk_tc_kernel     (one CTA per group; batch of 740 positions)
+full("trunk2")     # trunk_tc2_kernel<2> (CTA pair per group, 2 tiles per CTA; batch of 345 positions)
+full("trunk3")     # trunk_tc2_kernel<3> (CTA pair per group, 3 tiles per CTA; batch of 500 positions)
 full("tree")
