@@ -233,3 +233,25 @@ def test_largest_configuration_800_sims_matches_oracle(eng):
     for i in range(len(sts)):
         sc, cn, st = O.oracle_mcts(sts[i], 1.0, 800, 8)
         assert (counts[i, :ns[i]] == cn).all() and (scores[i, :ns[i]].view(np.uint32) == sc.view(np.uint32)).all()
+
+
+def test_full_size_cycle_500_games_every_game_bit_exact():
+    """BASELINE config 3 at full size under the hash evaluator: all 500 games of a self-play cycle (states, visit
+    counts, sampled actions, lengths, labels) are identical to the CPU oracle's"""
+    import engine
+    e = engine.Engine(n_slots=500, max_sims=50, max_batch=8, max_games=500)
+    try:
+        h = e.selfplay(500, sims=50, batch=8, seed=2025, evaluator=engine.EVAL_HASH, game0=0)
+        L = O.oracle()
+        st = np.zeros((81, 8), np.uint32); cn = np.zeros((81, 81), np.uint16)
+        ac = np.zeros(81, np.uint8); z = np.zeros(81, np.int8)
+        total = 0
+        for g in range(500):
+            n = L.orc_selfplay_hash(2025, g, 50, 8, st, cn, ac, z)
+            assert h.lens[g] == n, g
+            assert (h.states[g, :n] == st[:n]).all() and (h.counts[g, :n] == cn[:n]).all(), g
+            assert (h.actions[g, :n] == ac[:n]).all() and h.final[g] == (1 if z[0] == -1 else 0), g
+            total += n
+        assert h.stats[0] == total and h.stats[1] == 50 * total
+    finally:
+        e.close()

@@ -8,6 +8,8 @@ Tolerance (BASELINE.json north_star): |policy - ref| <= 1e-2, |value - ref| <= 1
     cannot meet 1e-2 on every position -- there we assert argmax agreement and the exceed fraction and
     print the statistics instead of silently loosening the bound.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -175,3 +177,50 @@ def test_drop_in_play_and_scores_api(setup):
     hist = self_play_cpp.play(model)
     assert 17 <= len(hist) <= 81 and hist[0][1].shape == (81,)
     assert [h[2] for h in hist[:2]] in ([-1, 1], [0, 0])
+
+
+def test_self_play_writes_reference_history_file(setup, tmp_path, monkeypatch):
+    """self_play_cpp.self_play(): ./model/best.pth in, ./data/<timestamp>.history out, loadable the way
+    train_network.py:21-60 loads it"""
+    import pickle
+    import torch
+    import self_play_cpp
+    from dual_network import dual_network
+    monkeypatch.chdir(tmp_path)
+    torch.manual_seed(1)
+    dual_network()                                        # creates ./model/best.pth (dual_network.py:124-135)
+    assert (tmp_path / "model" / "best.pth").exists()
+    monkeypatch.setattr(self_play_cpp, "SP_GAME_COUNT", 24)
+    np.random.seed(7)
+    path = self_play_cpp.self_play()
+    files = sorted((tmp_path / "data").glob("*.history"))
+    assert len(files) == 1 and str(files[0]).endswith(os.path.basename(path))
+    with open(files[0], "rb") as f:
+        history = pickle.load(f)
+    xs, ps, vs = zip(*history)                            # train_network.py:44-49
+    xs = np.array(xs).transpose(0, 3, 1, 2)
+    ps, vs = np.array(ps), np.array(vs)
+    assert xs.shape[1:] == (3, 9, 9) and xs.dtype == np.float32 and ps.shape[1] == 81 and ps.dtype == np.float64
+    assert len(history) == self_play_cpp.last_stats["plies"] and set(np.unique(vs)) <= {-1, 0, 1}
+    assert np.allclose(ps.sum(1), 1.0) and (ps[xs[:, 2].reshape(-1, 81)[:, _cell_to_action()] == 0] == 0).all()
+    # the tensor feed gives the same layout without the pickle
+    np.random.seed(7)
+    x, p, v = self_play_cpp.history_tensors(torch.load("./model/best.pth", weights_only=True) and _load_best(), 24)
+    assert x.shape[1:] == (3, 9, 9) and p.shape[1] == 81 and v.shape[1] == 1 and x.is_cuda
+
+
+def _cell_to_action():
+    # picture cell (R,C) -> action id, inverse used to index the policy by cell
+    R, C = np.divmod(np.arange(81), 9)
+    act = ((R // 3) * 3 + (C // 3)) * 9 + (R % 3) * 3 + (C % 3)
+    inv = np.zeros(81, np.int64)
+    inv[act] = np.arange(81)
+    return inv
+
+
+def _load_best():
+    import torch
+    from dual_network import DualNetwork
+    m = DualNetwork()
+    m.load_state_dict(torch.load("./model/best.pth", weights_only=True))
+    return m.eval()

@@ -118,6 +118,18 @@ def _run(model, n_games):
     return eng, hist
 
 
+def history_tensors(model, n_games=None):
+    """Trainer feed without the pickle round trip: runs a self-play cycle and returns CUDA tensors
+    in exactly the layout train_network.py:30-60 builds from the .history file:
+    xs (N,3,9,9) float32, policies (N,81) float32, values (N,1) float32."""
+    n_games = SP_GAME_COUNT if n_games is None else n_games
+    eng, hist = _run(model, n_games)
+    xs, pis, zs = _history_arrays(eng, hist)
+    dev = torch.device("cuda", eng.device)
+    x = torch.from_numpy(xs).to(dev).permute(0, 3, 1, 2).contiguous()
+    return x, torch.from_numpy(pis.astype(np.float32)).to(dev), torch.from_numpy(zs.astype(np.float32)).to(dev).unsqueeze(1)
+
+
 def play(model, use_cpp=True):
     """self_play_cpp.py:34-101: one game -> [[x, pi, z], ...]"""
     eng, hist = _run(model, 1)
