@@ -191,6 +191,7 @@ def test_self_play_writes_reference_history_file(setup, tmp_path, monkeypatch):
     dual_network()                                        # creates ./model/best.pth (dual_network.py:124-135)
     assert (tmp_path / "model" / "best.pth").exists()
     monkeypatch.setattr(self_play_cpp, "SP_GAME_COUNT", 24)
+    monkeypatch.setattr(self_play_cpp, "SP_WRITE_PACKED", True)
     np.random.seed(7)
     path = self_play_cpp.self_play()
     files = sorted((tmp_path / "data").glob("*.history"))
@@ -203,6 +204,10 @@ def test_self_play_writes_reference_history_file(setup, tmp_path, monkeypatch):
     assert xs.shape[1:] == (3, 9, 9) and xs.dtype == np.float32 and ps.shape[1] == 81 and ps.dtype == np.float64
     assert len(history) == self_play_cpp.last_stats["plies"] and set(np.unique(vs)) <= {-1, 0, 1}
     assert np.allclose(ps.sum(1), 1.0) and (ps[xs[:, 2].reshape(-1, 81)[:, _cell_to_action()] == 0] == 0).all()
+    # the packed sidecar decodes to the same training arrays
+    xs2, ps2, vs2 = self_play_cpp.load_packed_history(path.replace(".history", ".packed.npz"))
+    assert (xs2 == xs).all() and np.allclose(ps2, ps, atol=1e-7) and (vs2 == vs).all()
+    assert os.path.getsize(path.replace(".history", ".packed.npz")) < os.path.getsize(path) / 10
     # the tensor feed gives the same layout without the pickle
     np.random.seed(7)
     x, p, v = self_play_cpp.history_tensors(torch.load("./model/best.pth", weights_only=True) and _load_best(), 24)

@@ -1,0 +1,66 @@
+"""GPU: rows SURVEY 8(f) "next": the gating match and the vs-random evaluation on the engine."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _sequential_match(models, n_games, seed, temperature):
+    """evaluate_network.py:33-54,78-85 restated with one search per move through the single-position API"""
+    import uttt_cpp
+    import pv_mcts_cpp
+    points = []
+    for i in range(n_games):
+        rng = np.random.RandomState([seed & 0x7FFFFFFF, i])
+        order = models if i % 2 == 0 else tuple(reversed(models))
+        state = uttt_cpp.State()
+        while not state.is_done():
+            model = order[0] if state.is_first_player() else order[1]
+            sc = pv_mcts_cpp.pv_mcts_scores_cpp(model, state, temperature, 50, 8)
+            legal = state.legal_actions()
+            state = state.next(int(rng.choice(legal, p=sc / sc.sum())))
+        fp = (0 if state.is_first_player() else 1) if state.is_lose() else 0.5
+        points.append(fp if i % 2 == 0 else 1 - fp)
+    return points
+
+
+def test_gating_match_batched_equals_sequential():
+    import torch
+    import evaluate_network as en
+    from dual_network import DualNetwork
+    torch.manual_seed(1); m0 = DualNetwork().eval()
+    torch.manual_seed(2); m1 = DualNetwork().eval()
+    actors = (en.NetworkActor(m0, 1.0, 6), en.NetworkActor(m1, 1.0, 6))
+    try:
+        pts = en.play_matches(actors, 6, seed=77)
+    finally:
+        for a in actors:
+            a.close()
+    assert pts == _sequential_match((m0, m1), 6, 77, 1.0)
+    assert all(p in (0, 0.5, 1) for p in pts)
+
+
+def test_evaluate_network_and_best_player_scripts(tmp_path, monkeypatch, capsys):
+    import torch
+    import evaluate_network as en
+    import evaluate_best_player as ep
+    from dual_network import DualNetwork
+    monkeypatch.chdir(tmp_path)
+    (tmp_path / "model").mkdir()
+    torch.manual_seed(3); torch.save(DualNetwork().state_dict(), "./model/best.pth")
+    torch.manual_seed(4); torch.save(DualNetwork().state_dict(), "./model/latest.pth")
+    monkeypatch.setattr(en, "EN_GAME_COUNT", 8)
+    monkeypatch.setattr(en, "EN_SEED", 5)
+    promoted = en.evaluate_network()
+    out = capsys.readouterr().out
+    assert "AveragePoint" in out and ("Change BestPlayer" in out) == promoted
+    avg = float(out.split("AveragePoint")[1].split()[0])
+    assert promoted == (avg > 0.5)
+    if promoted:
+        a = torch.load("./model/best.pth", weights_only=True); b = torch.load("./model/latest.pth", weights_only=True)
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    monkeypatch.setattr(ep, "EP_GAME_COUNT", 4)
+    monkeypatch.setattr(ep, "EP_SEED", 9)
+    ep.evaluate_best_player()
+    out = capsys.readouterr().out
+    assert "VS_Random" in out and 0.0 <= float(out.split("VS_Random")[1].split()[0]) <= 1.0

@@ -38,6 +38,7 @@ SP_SEARCH_MODE = "compat"     # "compat": reference-exact search; "throughput": 
                               #   (evaluated root + Dirichlet noise, virtual loss, MCTS_BATCH_SIZE leaves / round)
 SP_DIRICHLET_ALPHA = 0.3      # throughput mode only
 SP_DIRICHLET_EPS = 0.25
+SP_WRITE_PACKED = False       # also write ./data/<timestamp>.packed.npz (357 B/sample instead of ~1.7 KB)
 
 _engine = None
 last_stats = {}
@@ -151,7 +152,26 @@ def self_play(use_cpp=True):
     os.makedirs("./data", exist_ok=True)
     with open(file_name, mode="wb") as f:
         pickle.dump(history, f)
+    if SP_WRITE_PACKED:
+        save_packed_history(file_name.replace(".history", ".packed.npz"), hist)
     return file_name
+
+
+def save_packed_history(path, hist):
+    """packed sidecar of a cycle: per sample the 32-byte position, the 81 visit counts and the label"""
+    st, cn, z = hist.samples()
+    np.savez_compressed(path, states=st, counts=cn, z=z, lens=hist.lens.copy(), final=hist.final.copy())
+
+
+def load_packed_history(path, device_index=0):
+    """-> (xs (N,3,9,9) f32, policies (N,81) f32, values (N,) f32) numpy arrays, i.e. what train_network.py:41-60
+    derives from the .history pickle (x planes are re-encoded on the GPU from the packed positions)"""
+    with np.load(path) as z:
+        st, cn, zz = z["states"], z["counts"], z["z"]
+    dev = torch.device("cuda", device_index)
+    xs = _eng.game_encode(torch.from_numpy(st.view(np.int32)).to(dev)).permute(0, 3, 1, 2).contiguous().cpu().numpy()
+    tot = cn.sum(axis=1, keepdims=True).astype(np.float32)
+    return xs, cn.astype(np.float32) / tot, zz.astype(np.float32)
 
 
 if __name__ == "__main__":
