@@ -118,6 +118,7 @@ struct NetWeights {
     __nv_bfloat16* res_w_bf16;
     __nv_bfloat16* conv_in_w_bf16;   // conv_input as a K=16-per-tap tensor-core layer: [12 taps (9 used)][2][128][8]
     float* bias_all;                 // [33][128]: conv_input shift followed by the 32 trunk layers' shifts
+    __nv_bfloat16* bias_blk;         // [33][2][128][8] bf16: each layer's shift as a tensor-core B block (hi, lo in k = 0, 1)
     float* head_w;                   // [3][128] policy conv (2 rows) + value conv, BN scale folded; [384..386] BN shifts
     // heads (fp32): policy conv [2][128] + shift[2], fc [81][162] + b; value conv [128] + shift, fc1 [256][81]+b, fc2 [256]+b
     float* pol_conv_w; float* pol_conv_b; float* pol_fc_w; float* pol_fc_b;

@@ -237,7 +237,7 @@ int uttt_destroy(uttt_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
-    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, e->w.head_w, e->w.pol_conv_w,
+    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, e->w.head_w, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b};
     for (float* p : wp) if (p) cudaFree(p);
@@ -345,6 +345,21 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
         if (!W.bias_all) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_all, 33 * 128 * sizeof(float)));
         UTTT_CUDA_OK(cudaMemcpy(W.bias_all, ci_b.data(), 128 * sizeof(float), cudaMemcpyHostToDevice));
         UTTT_CUDA_OK(cudaMemcpyAsync(W.bias_all + 128, W.res_b, 32 * 128 * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+        // bias blocks of the cluster trunk: shift = hi + lo (two bf16) against a constant (1,1,0,..) A row
+        std::vector<float> ball(33 * 128);
+        UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
+        UTTT_CUDA_OK(cudaMemcpy(ball.data(), W.bias_all, ball.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        std::vector<__nv_bfloat16> bb((size_t)33 * 2 * 128 * 8, __float2bfloat16(0.0f));
+        for (int l = 0; l < 33; l++)
+            for (int co = 0; co < 128; co++) {
+                float b = ball[l * 128 + co];
+                __nv_bfloat16 hi = __float2bfloat16(b);
+                __nv_bfloat16 lo = __float2bfloat16(b - __bfloat162float(hi));
+                bb[((size_t)l * 2 * 128 + co) * 8 + 0] = hi;
+                bb[((size_t)l * 2 * 128 + co) * 8 + 1] = lo;
+            }
+        if (!W.bias_blk) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_blk, bb.size() * sizeof(__nv_bfloat16)));
+        UTTT_CUDA_OK(cudaMemcpy(W.bias_blk, bb.data(), bb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
     }
     {
         std::vector<float> hw(387);

@@ -25,11 +25,7 @@
 // Warp roles: warps 0-15 epilogue, warp 16 weight producer, warps 17-20 MMA issuers (one elected lane each,
 // one accumulator tile each: a single issuing thread cannot keep the tensor pipe busy with K=16 MMAs of
 // 64 cycles because every issue costs ~80 cycles of descriptor/uniform-register traffic); warp 17 owns TMEM.
-#include <cuda_fp16.h>
-
-#include <type_traits>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace uttt {
 
@@ -54,140 +50,9 @@ constexpr int TC_THREADS = (17 + TC_ISSUERS) * 32;
 constexpr int TC_EPI_WARPS = 16;
 
 // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A and B, N=128, M=128
-constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t TC_IDESC = tcx::IDESC_M128_N128_BF16;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// shared-memory matrix descriptor, SWIZZLE_NONE, version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// bounded wait: a protocol bug must trap instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0) {
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (uint32_t it = 0;; it++) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (backoff_ns) __nanosleep(backoff_ns);     // keep pollers off the shared-memory port the MMA reads through
-        if ((it & 1023u) == 1023u) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ll) {
-                printf("uttt trunk_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                       threadIdx.x, bar, parity);
-                __trap();
-            }
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-// the skip connection is kept as fp16 (post-ReLU activations of a BatchNorm net are far inside the fp16
-// range, clamped anyway): 2 bytes per value like bf16 but 3 more mantissa bits, so the skip path does not add
-// a second bf16 rounding per block on top of the bf16 MMA operands.
-__device__ __forceinline__ void f16x8_add(const uint4& q, float* v) {
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float2 f = __half22float2(h[i]);
-        v[2 * i] += f.x;
-        v[2 * i + 1] += f.y;
-    }
-}
-// ReLU fused into the conversion (F2FP.RELU); fp16 conversion saturates
-__device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint32_t relu_f16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ void f16x8_add2(const uint4& q, float* v) {
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-    float2* v2 = reinterpret_cast<float2*>(v);
-#pragma unroll
-    for (int i = 0; i < 4; i++) v2[i] = __fadd2_rn(v2[i], __half22float2(h[i]));
-}
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-    __half2 h = __floats2half2_rn(fminf(lo, 65504.0f), fminf(hi, 65504.0f));
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
+using namespace tcx;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16

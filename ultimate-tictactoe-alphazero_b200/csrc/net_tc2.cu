@@ -19,11 +19,7 @@
 //
 // Warp roles (19 warps): 0-15 epilogue (2 tiles x 4 TMEM lane quarters x 2 column halves -- the epilogue is
 // instruction-latency bound, so it wants warps, not wider threads), 16 weight producer, 17-18 MMA issuers.
-#include <cuda_fp16.h>
-
-#include <type_traits>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace uttt {
 namespace tc2 {
@@ -33,9 +29,10 @@ constexpr int LEAD = 11;
 constexpr int STAGE_BYTES = 16384;
 constexpr int STAGES_PER_LAYER = 18;
 constexpr int IN_STAGES = 3;                    // conv_input: 9 taps x (K=16: 3 real channels) in 3 stages of 4 taps
-constexpr int GROUP_STAGES = IN_STAGES + NET_LAYERS * STAGES_PER_LAYER;
+constexpr int BIAS_BYTES = 4096;                // one [2 panels][128 co][8] block: BN shift as bf16 hi + lo in k = 0, 1
+constexpr int GROUP_STAGES = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);   // every layer starts with its bias block
 constexpr int GROUP_LAYERS = NET_LAYERS + 1;     // conv_input runs as layer -1 through the same pipeline
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t IDESC = tcx::IDESC_M128_N128_BF16;
 
 // LT = accumulator tiles per CTA.  LT=2: up to 5 positions per CTA pair (2+2 tiles), 8 weight stages.
 //                                   LT=3: up to 7 positions per CTA pair (3+3 tiles), 6 weight stages.
@@ -45,7 +42,7 @@ struct Cfg {
     static constexpr int MAX_P = (LT == 2) ? 5 : 7;
     static constexpr int AROWS = (LEAD + 128 * LT + 11 + 7) / 8 * 8;
     static constexpr int PANEL_BYTES = AROWS * 16;
-    static constexpr int A_BYTES = 16 * PANEL_BYTES;
+    static constexpr int A_BYTES = 18 * PANEL_BYTES;      // 16 channel panels + the constant panel pair of the bias MMA
     static constexpr int STAGES = (LT == 2) ? 8 : 6;
     static constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
     static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [128*LT rows][4] floats: head partial sums
@@ -56,171 +53,13 @@ struct Cfg {
     static constexpr uint32_t TMEM_COLS = (LT == 2) ? 256u : 512u;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, const uint4& v) {
-    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "r"(v.x), "r"(v.y), "r"(v.z),
-                 "r"(v.w)
-                 : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ uint32_t cluster_rank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-// bounded wait; traps instead of hanging.  CLUSTER = true acquires at cluster scope (needed where an arrival
-// comes from the peer CTA); ptxas then flushes L1 after the wait (CCTL.IVALL), so it is used only there.
-template <bool CLUSTER = false>
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t backoff_ns = 0) {
-    uint32_t ok = 0;
-    long long t0 = 0;
-    for (uint32_t it = 0;; it++) {
-        if (CLUSTER)
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok)
-                : "r"(bar), "r"(parity)
-                : "memory");
-        else
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(ok)
-                : "r"(bar), "r"(parity)
-                : "memory");
-        if (ok) return;
-        if (backoff_ns) __nanosleep(backoff_ns);
-        if ((it & 1023u) == 1023u) {
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ll) {
-                printf("uttt trunk_tc2: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-                       threadIdx.x, bar, parity);
-                __trap();
-            }
-        }
-    }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// arrive on the barrier at the same shared-memory offset in every CTA of `mask`
-__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-    uint32_t* r = reinterpret_cast<uint32_t*>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
-    __half2 h = __floats2half2_rn(fminf(lo, 65504.0f), fminf(hi, 65504.0f));
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void f16x8_add(const uint4& q, float* v) {
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        float2 f = __half22float2(h[i]);
-        v[2 * i] += f.x;
-        v[2 * i + 1] += f.y;
-    }
-}
-__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
-    return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-}
-__device__ __forceinline__ uint4 pack8_f16(const float* v) {
-    return make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
-}
-// ReLU fused into the conversion (F2FP.RELU): max(x,0) then round to bf16 / fp16 (saturating)
-__device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint32_t relu_f16x2(float lo, float hi) {
-    uint32_t d;
-    asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-    return d;
-}
-__device__ __forceinline__ uint4 relu_pack8_bf16(const float* v) {
-    return make_uint4(relu_bf16x2(v[0], v[1]), relu_bf16x2(v[2], v[3]), relu_bf16x2(v[4], v[5]), relu_bf16x2(v[6], v[7]));
-}
-__device__ __forceinline__ uint4 relu_pack8_f16(const float* v) {
-    return make_uint4(relu_f16x2(v[0], v[1]), relu_f16x2(v[2], v[3]), relu_f16x2(v[4], v[5]), relu_f16x2(v[6], v[7]));
-}
-// v[0..7] += 8 fp16 values (FADD2 pairs)
-__device__ __forceinline__ void f16x8_add2(const uint4& q, float* v) {
-    const __half2* h = reinterpret_cast<const __half2*>(&q);
-    float2* v2 = reinterpret_cast<float2*>(v);
-#pragma unroll
-    for (int i = 0; i < 4; i++) v2[i] = __fadd2_rn(v2[i], __half22float2(h[i]));
-}
+using namespace tcx;
 
 template <int LT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<LT>::THREADS, 1)
 trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
                  const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
-                 const float* __restrict__ bias,         // [33][128]: conv_input shift, then the 32 trunk layers
+                 const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
                  const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
                  const float* __restrict__ headw,        // [3][128] policy conv (2) + value conv, BN scale folded; [384..386] shifts
                  float* headfeat,                        // out: [rows][243] = relu(policy conv)[2][81], relu(value conv)[81]
@@ -279,6 +118,12 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // constant panel 16: every row = (1, 1, 0, ..., 0).  One extra K=16 MMA per tile and layer multiplies it with the
+    // layer's bias block (shift_hi, shift_lo in k = 0, 1), so the BatchNorm shift is added by the tensor pipe and the
+    // epilogue has no bias loads or adds (measured: -20 % epilogue time).
+    for (int i = threadIdx.x; i < C::AROWS; i += THREADS)
+        reinterpret_cast<uint4*>(sA + (size_t)16 * PANEL_BYTES)[i] = make_uint4(0x3F803F80u, 0, 0, 0);
     fence_async_all();
     tc_fence_before();
     __syncthreads();
@@ -359,7 +204,6 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 if (bnd) mbar_wait<true>(bar_bnd, lpar, 32);     // the peer's boundary-tile MMAs have retired
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
-                const float* bl = bias + (layer + 1) * 128 + chalf * 64;
                 float va[16], vb[16];
                 float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
                 tmem_ld16(taddr, va);
@@ -368,13 +212,6 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                     float* v = (ch & 1) ? vb : va;
                     tmem_ld_wait();
                     if (ch < 3) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
-                    float2* v2 = reinterpret_cast<float2*>(v);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 16) + j);
-                        v2[2 * j] = __fadd2_rn(v2[2 * j], make_float2(b4.x, b4.y));
-                        v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(b4.z, b4.w));
-                    }
                     f16x8_add2(sk[(2 * ch) % SKP], v);
                     f16x8_add2(sk[(2 * ch + 1) % SKP], v + 8);
                     if (SKP == 4 && ch < 2 && second && valid) {     // refill the two registers just consumed: panels +4
@@ -433,18 +270,26 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
             // ================= weight producer =================
             if (tiles == 0) continue;
 #pragma unroll 1
-            for (int n = 0; n < GROUP_STAGES; n++) {
-                const int gn = iter * GROUP_STAGES + n;
-                const int stage = gn % STAGES;
-                const uint32_t par = (uint32_t)((gn / STAGES) & 1);
-                mbar_wait(bar_empty + 8 * stage, par ^ 1u);
-                if (lane == 0) {
-                    mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-                    const __nv_bfloat16* src = (n < IN_STAGES) ? wq_in + (size_t)n * (STAGE_BYTES / 2)
-                                                               : wq + (size_t)(n - IN_STAGES) * (STAGE_BYTES / 2);
-                    bulk_g2s(sB_u + stage * STAGE_BYTES, src, STAGE_BYTES, bar_full + 8 * stage);
+            int gn = iter * GROUP_STAGES;
+#pragma unroll 1
+            for (int layer = -1; layer < NET_LAYERS; layer++) {
+                const int n_st = 1 + ((layer < 0) ? IN_STAGES : STAGES_PER_LAYER);
+#pragma unroll 1
+                for (int st = 0; st < n_st; st++, gn++) {
+                    const int stage = gn % STAGES;
+                    const uint32_t par = (uint32_t)((gn / STAGES) & 1);
+                    mbar_wait(bar_empty + 8 * stage, par ^ 1u);
+                    if (lane == 0) {
+                        const __nv_bfloat16* src;
+                        uint32_t bytes = STAGE_BYTES;
+                        if (st == 0) { src = wq_bias + (size_t)(layer + 1) * (BIAS_BYTES / 2); bytes = BIAS_BYTES; }
+                        else if (layer < 0) src = wq_in + (size_t)(st - 1) * (STAGE_BYTES / 2);
+                        else src = wq + (size_t)(layer * STAGES_PER_LAYER + st - 1) * (STAGE_BYTES / 2);
+                        mbar_expect_tx(bar_full + 8 * stage, bytes);
+                        bulk_g2s(sB_u + stage * STAGE_BYTES, src, bytes, bar_full + 8 * stage);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         } else {
             // ================= MMA issuers: warp 9+t drives local accumulator tile t =================
@@ -462,8 +307,9 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 fence_async_all();
                 tc_fence_after();
                 if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0) dbg[layer * 4 + 0] = clock64();
-                const int n_st = (layer < 0) ? IN_STAGES : STAGES_PER_LAYER;
-                const int st0 = iter * GROUP_STAGES + ((layer < 0) ? 0 : IN_STAGES + layer * STAGES_PER_LAYER);
+                const int n_st = 1 + ((layer < 0) ? IN_STAGES : STAGES_PER_LAYER);
+                const int st0 = iter * GROUP_STAGES +
+                                ((layer < 0) ? 0 : (IN_STAGES + 1) + layer * (STAGES_PER_LAYER + 1));
 #pragma unroll 1
                 for (int s = 0; s < n_st; s++) {
                     const int gn = st0 + s;
@@ -473,25 +319,29 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                     tc_fence_after();
                     if (leader) {
                         const uint32_t b0 = sB_u + (uint32_t)stage * STAGE_BYTES;
-                        if (layer < 0) {
-                            // conv_input: block j of stage s is tap 4s+j, K = 16 (channel panels 0,1)
+                        if (s == 0) {
+                            // accumulator := BN shift (constant panel x bias block); starts the layer's accumulation
+                            umma_bf16(tmem_d, make_desc(a_tile + 16u * PANEL_BYTES, PANEL_BYTES, 128), make_desc(b0, 2048, 128),
+                                      IDESC, 0u);
+                        } else if (layer < 0) {
+                            // conv_input: block j of stage s is tap 4(s-1)+j, K = 16 (channel panels 0,1)
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const int tap = 4 * s + j;
+                                const int tap = 4 * (s - 1) + j;
                                 if (tap < 9) {
                                     const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
                                     umma_bf16(tmem_d, make_desc(a_tile + (uint32_t)(shift * 16), PANEL_BYTES, 128),
-                                              make_desc(b0 + (uint32_t)j * 4096u, 2048, 128), IDESC, (uint32_t)(tap != 0));
+                                              make_desc(b0 + (uint32_t)j * 4096u, 2048, 128), IDESC, 1u);
                                 }
                             }
                         } else {
-                            const int tap = s >> 1, half = s & 1;
+                            const int tap = (s - 1) >> 1, half = (s - 1) & 1;
                             const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * PANEL_BYTES;
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) {
                                 umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * PANEL_BYTES, PANEL_BYTES, 128),
-                                          make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), IDESC, (uint32_t)((s | ks) != 0));
+                                          make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), IDESC, 1u);
                             }
                         }
                         umma_commit(bar_empty + 8 * stage);
@@ -537,12 +387,12 @@ cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, f
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
     const int cap2 = (n_sm / 2) * tc2::Cfg<2>::MAX_P, cap3 = (n_sm / 2) * tc2::Cfg<3>::MAX_P;
     tc2::trunk_tc2_kernel<2><<<2 * pairs, tc2::Cfg<2>::THREADS, tc2::Cfg<2>::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, 0,
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_blk, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, 0,
         cap2, dbg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || max_rows <= cap2) return e;
     tc2::trunk_tc2_kernel<3><<<2 * pairs, tc2::Cfg<3>::THREADS, tc2::Cfg<3>::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, cap2,
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_blk, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, cap2,
         cap3, dbg);
     return cudaGetLastError();
 }
