@@ -36,12 +36,13 @@ constexpr int TC_M = 128 * TC_TILES;          // 512 GEMM rows per group
 constexpr int TC_LEAD = 11;                   // zero rows before row 0 (largest negative shift)
 constexpr int TC_AROWS = 536;                 // >= TC_LEAD + 512 + 11
 constexpr int TC_PANEL_BYTES = TC_AROWS * 16; // one 8-channel panel
-constexpr int TC_A_BYTES = 16 * TC_PANEL_BYTES;
+constexpr int TC_A_BYTES = 18 * TC_PANEL_BYTES;   // 16 channel panels + the constant panel pair of the bias MMA
 constexpr int TC_STAGE_BYTES = 16384;         // half a tap: 64 ci x 128 co bf16
-constexpr int TC_STAGES = 5;
+constexpr int TC_STAGES = 4;
 constexpr int TC_STAGES_PER_LAYER = 18;
 constexpr int TC_IN_STAGES = 3;                // conv_input: 9 taps x (K=16: 3 real channels) in 3 stages of 4 taps
-constexpr int TC_GROUP_STAGES = TC_IN_STAGES + NET_LAYERS * TC_STAGES_PER_LAYER;
+constexpr int TC_BIAS_BYTES = 4096;             // [2 panels][128 co][8]: BN shift as bf16 hi + lo in k = 0, 1
+constexpr int TC_GROUP_STAGES = (TC_IN_STAGES + 1) + NET_LAYERS * (TC_STAGES_PER_LAYER + 1);   // each layer starts with its bias block
 constexpr int TC_GROUP_LAYERS = NET_LAYERS + 1;  // conv_input runs as layer -1 through the same pipeline
 constexpr int TC_BAR_OFF = TC_A_BYTES + TC_STAGES * TC_STAGE_BYTES;
 constexpr int TC_SMEM_BYTES = TC_BAR_OFF + 256;
@@ -57,7 +58,7 @@ using namespace tcx;
 __global__ void __launch_bounds__(TC_THREADS, 1)
 trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
-                const float* __restrict__ bias,         // [33][128]: conv_input shift, then the 32 trunk layers
+                const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
                 const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
                 const float* __restrict__ headw,        // [3][128] head 1x1 convs (BN scale folded) + [384..386] shifts
                 float* headfeat,                        // out: [rows][243] = relu(policy conv)[2][81], relu(value conv)[81]
@@ -109,6 +110,10 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
     }
     // zero the whole activation buffer once: lead/tail margins and padding rows stay zero forever
     for (int i = threadIdx.x; i < TC_A_BYTES / 16; i += TC_THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // constant panel 16, every row = (1, 1, 0, ..., 0): the A operand of the per-layer bias MMA (see net_tc2.cu)
+    for (int i = threadIdx.x; i < TC_AROWS; i += TC_THREADS)
+        reinterpret_cast<uint4*>(sA + (size_t)16 * TC_PANEL_BYTES)[i] = make_uint4(0x3F803F80u, 0, 0, 0);
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -173,7 +178,6 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 if (nb_hi) mbar_wait(bar_accum + 8 * (tile + 1), lpar, 64);
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
-                const float* bl = bias + (layer + 1) * 128;
                 // 8 chunks of 16 accumulator columns, TMEM loads double-buffered against the math / stores
                 float va[16], vb[16];
                 float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
@@ -183,13 +187,6 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                     float* v = (ch & 1) ? vb : va;
                     tmem_ld_wait();
                     if (ch < 7) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
-                    float2* v2 = reinterpret_cast<float2*>(v);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        float4 b4 = __ldg(reinterpret_cast<const float4*>(bl + ch * 16) + j);
-                        v2[2 * j] = __fadd2_rn(v2[2 * j], make_float2(b4.x, b4.y));
-                        v2[2 * j + 1] = __fadd2_rn(v2[2 * j + 1], make_float2(b4.z, b4.w));
-                    }
                     f16x8_add2(sk[(2 * ch) & 7], v);
                     f16x8_add2(sk[(2 * ch + 1) & 7], v + 8);
                     if (ch < 4 && second && valid) {             // refill the two registers just consumed: panels +8
@@ -243,18 +240,26 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
         } else if (warp == 16) {
             // ================= weight producer =================
 #pragma unroll 1
-            for (int n = 0; n < TC_GROUP_STAGES; n++) {
-                const int gn = iter * TC_GROUP_STAGES + n;
-                const int stage = gn % TC_STAGES;
-                const uint32_t par = (uint32_t)((gn / TC_STAGES) & 1);
-                mbar_wait(bar_empty + 8 * stage, par ^ 1u);
-                if (lane == 0) {
-                    mbar_expect_tx(bar_full + 8 * stage, TC_STAGE_BYTES);
-                    const __nv_bfloat16* src = (n < TC_IN_STAGES) ? wq_in + (size_t)n * (TC_STAGE_BYTES / 2)
-                                                                  : wq + (size_t)(n - TC_IN_STAGES) * (TC_STAGE_BYTES / 2);
-                    bulk_g2s(sB_u + stage * TC_STAGE_BYTES, src, TC_STAGE_BYTES, bar_full + 8 * stage);
+            int gn = iter * TC_GROUP_STAGES;
+#pragma unroll 1
+            for (int layer = -1; layer < NET_LAYERS; layer++) {
+                const int n_st = 1 + ((layer < 0) ? TC_IN_STAGES : TC_STAGES_PER_LAYER);
+#pragma unroll 1
+                for (int st = 0; st < n_st; st++, gn++) {
+                    const int stage = gn % TC_STAGES;
+                    const uint32_t par = (uint32_t)((gn / TC_STAGES) & 1);
+                    mbar_wait(bar_empty + 8 * stage, par ^ 1u);
+                    if (lane == 0) {
+                        const __nv_bfloat16* src;
+                        uint32_t bytes = TC_STAGE_BYTES;
+                        if (st == 0) { src = wq_bias + (size_t)(layer + 1) * (TC_BIAS_BYTES / 2); bytes = TC_BIAS_BYTES; }
+                        else if (layer < 0) src = wq_in + (size_t)(st - 1) * (TC_STAGE_BYTES / 2);
+                        else src = wq + (size_t)(layer * TC_STAGES_PER_LAYER + st - 1) * (TC_STAGE_BYTES / 2);
+                        mbar_expect_tx(bar_full + 8 * stage, bytes);
+                        bulk_g2s(sB_u + stage * TC_STAGE_BYTES, src, bytes, bar_full + 8 * stage);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         } else {
             // ================= MMA issuers: warp 17+t drives accumulator tile t =================
@@ -268,8 +273,9 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                 mbar_wait(bar_act + 8 * tile, (uint32_t)((iter * TC_GROUP_LAYERS + layer + 1) & 1), 32);
                 tc_fence_after();
                 if (dbg && blockIdx.x == 0 && iter == 0 && tile == 0 && leader && layer >= 0) dbg[layer * 4 + 0] = clock64();
-                const int n_st = (layer < 0) ? TC_IN_STAGES : TC_STAGES_PER_LAYER;
-                const int st0 = iter * TC_GROUP_STAGES + ((layer < 0) ? 0 : TC_IN_STAGES + layer * TC_STAGES_PER_LAYER);
+                const int n_st = 1 + ((layer < 0) ? TC_IN_STAGES : TC_STAGES_PER_LAYER);
+                const int st0 = iter * TC_GROUP_STAGES +
+                                ((layer < 0) ? 0 : (TC_IN_STAGES + 1) + layer * (TC_STAGES_PER_LAYER + 1));
 #pragma unroll 1
                 for (int s = 0; s < n_st; s++) {
                     const int gn = st0 + s;
@@ -279,25 +285,29 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                     tc_fence_after();
                     if (leader) {
                         const uint32_t b0 = sB_u + (uint32_t)stage * TC_STAGE_BYTES;
-                        if (layer < 0) {
-                            // conv_input: block j of stage s is tap 4s+j, K = 16 (channel panels 0,1)
+                        if (s == 0) {
+                            // accumulator := BN shift (constant panel x bias block); starts the layer's accumulation
+                            umma_bf16(tmem_d, make_desc(a_tile + 16u * TC_PANEL_BYTES, TC_PANEL_BYTES, 128),
+                                      make_desc(b0, 2048, 128), TC_IDESC, 0u);
+                        } else if (layer < 0) {
+                            // conv_input: block j of stage s is tap 4(s-1)+j, K = 16 (channel panels 0,1)
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const int tap = 4 * s + j;
+                                const int tap = 4 * (s - 1) + j;
                                 if (tap < 9) {
                                     const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
                                     umma_bf16(tmem_d, make_desc(a_tile + (uint32_t)(shift * 16), TC_PANEL_BYTES, 128),
-                                              make_desc(b0 + (uint32_t)j * 4096u, 2048, 128), TC_IDESC, (uint32_t)(tap != 0));
+                                              make_desc(b0 + (uint32_t)j * 4096u, 2048, 128), TC_IDESC, 1u);
                                 }
                             }
                         } else {
-                            const int tap = s >> 1, half = s & 1;
+                            const int tap = (s - 1) >> 1, half = (s - 1) & 1;
                             const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
                             const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * TC_PANEL_BYTES;
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) {
                                 umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * TC_PANEL_BYTES, TC_PANEL_BYTES, 128),
-                                          make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), TC_IDESC, (uint32_t)((s | ks) != 0));
+                                          make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), TC_IDESC, 1u);
                             }
                         }
                         umma_commit(bar_empty + 8 * stage);          // frees the weight stage when the MMAs retire
@@ -329,7 +339,7 @@ cudaError_t launch_trunk_tc(const NetWeights& w, const __nv_bfloat16* planes, fl
                             int max_rows, float* resid, int n_sm, cudaStream_t s, long long* dbg, int min_count) {
     int grid = max_rows < n_sm ? max_rows : n_sm;
     if (grid < 1) grid = 1;
-    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.conv_in_w_bf16, w.bias_all, planes, w.head_w, headfeat, resid,
+    trunk_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, s>>>(w.res_w_bf16, w.conv_in_w_bf16, w.bias_blk, planes, w.head_w, headfeat, resid,
                                                             count, min_count, dbg);
     return cudaGetLastError();
 }
