@@ -162,6 +162,33 @@ def gen_boltzman():
     np.savez_compressed(os.path.join(OUT, "boltzman.npz"), xs=xs, **out)
 
 
+def gen_network():
+    """fp32 outputs of the REFERENCE DualNetwork (dual_network.py, imported from /root/reference) with its own
+    random init under torch.manual_seed(0), on positions from Philox playouts (planes from the reference State)."""
+    import importlib.util
+    import torch
+    spec = importlib.util.spec_from_file_location("ref_dual_network", "/root/reference/dual_network.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(0)
+    model = ref.DualNetwork().eval()
+    R = O.ref()
+    states = np.concatenate([O.playout_states(SEED + 3, g)[0][:-1:3] for g in range(10)])[:160]
+    planes = np.zeros((len(states), 243), np.float32)
+    for i, w in enumerate(states):
+        f, n_ = C.c_int(), C.c_int()
+        R.ref_state_probe(w, C.byref(f), C.byref(n_), np.zeros(81, np.int32), planes[i])
+    x = torch.from_numpy(planes.reshape(-1, 9, 9, 3)).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        p, v = model(x)
+    sd = model.state_dict()
+    digest = float(sum(t.double().abs().sum() for t in sd.values()))
+    np.savez_compressed(os.path.join(OUT, "network.npz"), states=states, policy=p.numpy(), value=v.numpy()[:, 0],
+                        n_params=np.int64(sum(t.numel() for t in model.parameters())), n_entries=np.int64(len(sd)),
+                        weight_abs_sum=np.float64(digest), torch_version=np.array(torch.__version__))
+    print("network.npz:", len(states), "positions; params", sum(t.numel() for t in model.parameters()))
+
+
 if __name__ == "__main__":
     if not O.ref_available():
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
@@ -170,3 +197,4 @@ if __name__ == "__main__":
     gen_mcts()
     gen_selfplay()
     gen_boltzman()
+    gen_network()

@@ -127,3 +127,22 @@ def test_history_labels_follow_reference_rule():
     assert len(z) == 9
     # self_play_cpp.py:95-99: z0 = -1 if final.is_lose() else 0, alternating from ply 0
     assert z.tolist() == [-1, 1, -1, -1, 1, -1, 1, 0, 0]
+
+
+def test_dual_network_reproduces_reference_golden_outputs(golden_dir):
+    """same seed -> same weights and same fp32 outputs as the reference's own DualNetwork (tests/golden/network.npz,
+    generated by importing /root/reference/dual_network.py in oracle/gen_golden.py)"""
+    import torch
+    from dual_network import DualNetwork
+    with np.load(os.path.join(golden_dir, "network.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    torch.manual_seed(0)
+    m = DualNetwork().eval()
+    sd = m.state_dict()
+    assert len(sd) == int(g["n_entries"]) and sum(t.numel() for t in m.parameters()) == int(g["n_params"])
+    assert abs(float(sum(t.double().abs().sum() for t in sd.values())) - float(g["weight_abs_sum"])) < 1e-6
+    planes = np.stack([O.oracle_probe(w)[2] for w in g["states"]]).reshape(-1, 9, 9, 3)
+    x = torch.from_numpy(planes).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        p, v = m(x)
+    assert np.abs(p.numpy() - g["policy"]).max() < 1e-5 and np.abs(v.numpy()[:, 0] - g["value"]).max() < 1e-5

@@ -229,3 +229,19 @@ def _load_best():
     m = DualNetwork()
     m.load_state_dict(torch.load("./model/best.pth", weights_only=True))
     return m.eval()
+
+
+def test_fp32_trunk_vs_reference_golden_outputs(setup, golden_dir):
+    """engine forward (fp32 numerics) vs outputs of the REFERENCE's own DualNetwork on its seed-0 random init"""
+    import engine
+    e, model, sts = setup          # `model` is DualNetwork() under torch.manual_seed(0): the golden's weights
+    with np.load(os.path.join(golden_dir, "network.npz")) as z:
+        g = {k: z[k] for k in z.files}
+    e.upload_model(model)
+    p, v = _forward(e, g["states"], engine.EVAL_NET_FP32)
+    assert np.abs(p - g["policy"]).max() <= TOL and np.abs(v - g["value"]).max() <= TOL
+    pb, vb = _forward(e, g["states"], engine.EVAL_NET_BF16)
+    print("vs reference golden: fp32 max|dp|=%.2e max|dv|=%.2e ; bf16 argmax agreement %.3f max|dv|=%.2e" % (
+        np.abs(p - g["policy"]).max(), np.abs(v - g["value"]).max(), (pb.argmax(1) == g["policy"].argmax(1)).mean(),
+        np.abs(vb - g["value"]).max()))
+    assert (pb.argmax(1) == g["policy"].argmax(1)).mean() >= 0.9
