@@ -245,3 +245,28 @@ def test_fp32_trunk_vs_reference_golden_outputs(setup, golden_dir):
         np.abs(p - g["policy"]).max(), np.abs(v - g["value"]).max(), (pb.argmax(1) == g["policy"].argmax(1)).mean(),
         np.abs(vb - g["value"]).max()))
     assert (pb.argmax(1) == g["policy"].argmax(1)).mean() >= 0.9
+
+
+def test_trunk_variant_boundaries_give_identical_rows(setup):
+    """The trunk kernel is chosen on the device from the batch size (CTA pairs with 2 or 3 tiles, or one CTA per group)
+    and the group size from ceil(n / pairs): every boundary of that dispatch must produce the same rows."""
+    import engine
+    e, model, sts = setup
+    e2 = engine.Engine(n_slots=800, max_sims=50, max_batch=8, max_games=8)
+    try:
+        e2.upload_model(model)
+        big = np.concatenate([sts, sts])[:800]
+        ref_p, ref_v = _forward(e2, big, engine.EVAL_NET_BF16)            # one CTA per group (n > 518)
+        pair_p, pair_v = _forward(e2, big[:518], engine.EVAL_NET_BF16)    # CTA pairs, 3 tiles per CTA
+        # the two families sum the heads' 1x1 convs in a different order (whole row vs two column halves); on the
+        # ill-conditioned random-init net (logits up to +-400) that fp32 reordering shows up at the 1e-5 level
+        assert np.abs(pair_p - ref_p[:518]).max() < 1e-3 and np.abs(pair_v - ref_v[:518]).max() < 1e-3
+        f32_p, _ = _forward(e2, big[:64], engine.EVAL_NET_FP32)
+        assert (ref_p[:64].argmax(1) == f32_p.argmax(1)).mean() > 0.9
+        for n in (2, 3, 73, 74, 75, 147, 148, 149, 221, 222, 223, 295, 296, 297, 369, 370, 371, 372, 443, 444, 445,
+                  517, 518, 519, 520, 739, 740, 741, 800):
+            p, v = _forward(e2, big[:n], engine.EVAL_NET_BF16)
+            rp, rv = (pair_p, pair_v) if n <= 518 else (ref_p, ref_v)
+            assert (p == rp[:n]).all() and (v == rv[:n]).all(), n
+    finally:
+        e2.close()
