@@ -1,0 +1,56 @@
+"""Rules kernels at BASELINE config-2 scale: CUDA-event timings + algorithmic GB/s (python tools/prof_rules.py [log2_n])."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "ultimate-tictactoe-alphazero_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import engine  # noqa: E402
+import oracle_lib as O  # noqa: E402
+
+lg = int(sys.argv[1]) if len(sys.argv) > 1 else 22
+n = 1 << lg
+base = np.concatenate([O.playout_states(5, g)[0][:-1] for g in range(64)])
+states = torch.from_numpy(np.resize(base, (n, 8)).view(np.int32).copy()).cuda()        # 128 MiB at 2^22: larger than L2
+masks, status = engine.game_legal_mask(states)
+acts = torch.zeros(n, dtype=torch.int32, device="cuda")
+m = masks.cpu().numpy().view(np.uint32)
+first = np.where(m[:, 0] != 0, np.log2(m[:, 0] & -m[:, 0].astype(np.int64)).astype(np.int32),
+                 np.where(m[:, 1] != 0, 27 + np.log2(m[:, 1] & -m[:, 1].astype(np.int64)).astype(np.int32),
+                          54 + np.log2(np.maximum(m[:, 2], 1) & -np.maximum(m[:, 2], 1).astype(np.int64)).astype(np.int32)))
+acts.copy_(torch.from_numpy(first.astype(np.int32)))
+
+
+def timed(fn, reps=5):
+    fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+out = {"n_states": n}
+for name, fn, bytes_per in (
+        ("step_kernel", lambda: engine.game_step(states, acts), 32 + 4 + 32),
+        ("legal_kernel", lambda: engine.game_legal_mask(states), 32 + 16 + 1),
+        ("encode_kernel", lambda: engine.game_encode(states[: n // 4]), None),
+        ("gather_planes_kernel", lambda: engine.game_gather_planes(states[: n // 4]), None)):
+    ms = timed(fn)
+    if bytes_per is None:
+        cnt = n // 4
+        bytes_per = 32 + (972 if name == "encode_kernel" else 486)
+    else:
+        cnt = n
+    out[name] = {"ms": ms, "states": cnt, "algorithmic_bytes_per_state": bytes_per,
+                 "GBps": cnt * bytes_per / (ms / 1e3) / 1e9, "frac_of_measured_hbm_6551": cnt * bytes_per / (ms / 1e3) / 1e9 / 6551.0}
+ms = timed(lambda: engine.game_playout(0x5EED, 0, 1 << 20), reps=3)
+dg, pl, rs = engine.game_playout(0x5EED, 0, 1 << 20)
+out["playout_kernel"] = {"ms": ms, "games": 1 << 20, "transitions": int(pl.sum().item()),
+                         "transitions_per_s": int(pl.sum().item()) / (ms / 1e3)}
+print(json.dumps(out, indent=1))
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "rules_points.json"), "w"), indent=1)

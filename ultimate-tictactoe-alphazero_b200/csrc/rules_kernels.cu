@@ -58,47 +58,54 @@ __global__ void __launch_bounds__(256) legal_kernel(const PackedState* __restric
     if (status) status[i] = (uint8_t)status_of(s, cnt);
 }
 
-// cpp/uttt_game.cpp:244-280: float HWC (9,9,3); one thread per output element -> coalesced stores,
-// the 32-byte state is re-read through L1 by the 243 threads that share it.
-__global__ void __launch_bounds__(256) encode_kernel(const PackedState* __restrict__ in, float* __restrict__ planes,
-                                                     int64_t n) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * 243) return;
-    int64_t i = idx / 243;
-    int e = (int)(idx - i * 243);
-    int cell = e / 3, ch = e - 3 * cell;
-    int a = action_of_rc(cell / 9, cell % 9);
-    PackedState s = load_state(in + i);
-    bool v;
-    if (ch == 0) v = stone_me(s, a);
-    else if (ch == 1) v = stone_opp(s, a);
-    else {
-        uint32_t lm[3];
-        legal_mask(s, lm);
-        v = legal_bit(lm, a);
-    }
-    planes[idx] = v ? 1.0f : 0.0f;
+// The 27 nine-bit picture rows of a position (3 planes x 9 rows), one per lane: lane 9*plane + R holds row R of
+// plane (0 mover, 1 opponent, 2 legal).  Elements are then fetched with one shuffle each.
+__device__ __forceinline__ uint32_t warp_picture_rows(const PackedState& s, int lane) {
+    uint32_t lm[3];
+    legal_mask(s, lm);
+    int plane = lane / 9, R = lane - 9 * plane;
+    uint32_t x[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) x[j] = (plane == 0) ? s.w[j] : (plane == 1 ? s.w[3 + j] : lm[j]);
+    return (lane < 27) ? picture_row(x, R) : 0u;
 }
 
-// leaf gather (pv_mcts_cpp.py:47-60): bf16 CHW (3,9,9) rows of the network's input batch
+// cpp/uttt_game.cpp:244-280: float HWC (9,9,3).  One warp per position: the 32-byte state is loaded once, the legal
+// mask and the 27 picture rows are computed once per warp, every store instruction of the warp writes 128 contiguous
+// bytes.  HBM-bound by design: 32 B in, 972 B out per position.
+__global__ void __launch_bounds__(256) encode_kernel(const PackedState* __restrict__ in, float* __restrict__ planes,
+                                                     int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    uint32_t rows = warp_picture_rows(load_state(in + i), lane);
+    float* out = planes + i * 243;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int e = lane + 32 * k;                  // e = (R*9 + C)*3 + ch
+        int cell = e / 3, ch = e - 3 * cell;
+        int R = cell / 9, C = cell - 9 * R;
+        uint32_t m = __shfl_sync(0xFFFFFFFFu, rows, (9 * ch + R) & 31);
+        if (e < 243) out[e] = (float)((m >> C) & 1u);
+    }
+}
+
+// leaf gather (pv_mcts_cpp.py:47-60): bf16 CHW (3,9,9) rows of the network's input batch; same warp-per-position
+// scheme, 32 B in, 486 B out per position.
 __global__ void __launch_bounds__(256) gather_planes_kernel(const PackedState* __restrict__ in,
                                                             __nv_bfloat16* __restrict__ planes, int64_t n) {
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * 243) return;
-    int64_t i = idx / 243;
-    int e = (int)(idx - i * 243);
-    int ch = e / 81, cell = e - 81 * ch;
-    int a = action_of_rc(cell / 9, cell % 9);
-    PackedState s = load_state(in + i);
-    bool v;
-    if (ch == 0) v = stone_me(s, a);
-    else if (ch == 1) v = stone_opp(s, a);
-    else {
-        uint32_t lm[3];
-        legal_mask(s, lm);
-        v = legal_bit(lm, a);
+    int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    uint32_t rows = warp_picture_rows(load_state(in + i), lane);
+    __nv_bfloat16* out = planes + i * 243;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int e = lane + 32 * k;                  // e = ch*81 + R*9 + C  ->  row index e/9 = 9*ch + R
+        int row = e / 9, C = e - 9 * row;
+        uint32_t m = __shfl_sync(0xFFFFFFFFu, rows, row & 31);
+        if (e < 243) out[e] = __ushort_as_bfloat16(((m >> C) & 1u) ? (unsigned short)0x3F80 : (unsigned short)0);
     }
-    planes[idx] = __float2bfloat16(v ? 1.0f : 0.0f);
 }
 
 // Whole random games with the state in registers: HBM traffic is 16 B out per game, the kernel is
@@ -273,14 +280,14 @@ int uttt_game_legal_mask(const uint32_t* states, uint32_t* masks, uint8_t* statu
 
 int uttt_game_encode(const uint32_t* states, float* planes, int64_t n, void* stream) {
     if (n <= 0) return 0;
-    encode_kernel<<<ceil_div(n * 243, 256), 256, 0, (cudaStream_t)stream>>>((const PackedState*)states, planes, n);
+    encode_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>((const PackedState*)states, planes, n);
     UTTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int uttt_game_gather_planes(const uint32_t* states, void* planes, int64_t n, void* stream) {
     if (n <= 0) return 0;
-    gather_planes_kernel<<<ceil_div(n * 243, 256), 256, 0, (cudaStream_t)stream>>>(
+    gather_planes_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(
         (const PackedState*)states, (__nv_bfloat16*)planes, n);
     UTTT_CUDA_OK(cudaGetLastError());
     return 0;

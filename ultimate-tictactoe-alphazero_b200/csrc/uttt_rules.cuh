@@ -153,6 +153,15 @@ UTTT_HD int legal_rank(const uint32_t lm[3], int a) {
     return r + popc32(w & ((1u << bit) - 1u));
 }
 
+// 9 cells of picture row R (bit C = column C) taken from three words holding 3 sub-boards x 9 cells each
+// (the mover / opponent / legal-mask words): sub-board row R/3, cell row R%3 of its three sub-boards.
+UTTT_HD uint32_t picture_row(const uint32_t x[3], int R) {
+    int br = R / 3, sr = R - 3 * br;
+    uint32_t w = (br == 0) ? x[0] : (br == 1 ? x[1] : x[2]);
+    w >>= 3 * sr;
+    return (w & 7u) | (((w >> 9) & 7u) << 3) | (((w >> 18) & 7u) << 6);
+}
+
 // cell (R,C) of the 9x9 picture <-> (board, cell): cpp/uttt_game.cpp:256-257
 UTTT_HD int action_of_rc(int R, int C) { return ((R / 3) * 3 + (C / 3)) * 9 + (R % 3) * 3 + (C % 3); }
 
