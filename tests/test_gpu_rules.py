@@ -97,3 +97,33 @@ def test_rules_kernels_ragged_and_empty():
         for i in (0, n // 2, n - 1):
             flags, legal, _ = O.oracle_probe(sts[i])
             assert [a for a in range(81) if (m[i, a // 27] >> (a % 27)) & 1] == legal.tolist()
+
+
+def test_encode_gather_ragged_and_unaligned(rules):
+    """plane writers: sizes around the 256-position block, and destinations off the 16-byte grid (other kernel)"""
+    import torch
+    import engine
+    reps = 3
+    sts = np.concatenate([rules["states"]] * reps)
+    ref = np.concatenate([rules["tensor"]] * reps).astype(np.float32)             # (n,243) HWC
+    ref_chw = ref.reshape(-1, 9, 9, 3).transpose(0, 3, 1, 2).reshape(-1, 243)
+    st = _dev(sts.view(np.int32))
+    for n in (1, 3, 255, 256, 257, 511, 1000, len(sts)):
+        assert (engine.game_encode(st[:n]).cpu().numpy().reshape(n, 243) == ref[:n]).all()
+        assert (engine.game_gather_planes(st[:n]).float().cpu().numpy().reshape(n, 243) == ref_chw[:n]).all()
+        for off in (1, 2, 3):
+            buf = torch.full((n * 243 + 8,), -7.0, dtype=torch.float32, device="cuda")
+            engine.game_encode(st[:n], out=buf[off:off + n * 243])
+            b = buf.cpu().numpy()
+            assert (b[off:off + n * 243].reshape(n, 243) == ref[:n]).all()
+            assert (b[:off] == -7.0).all() and (b[off + n * 243:] == -7.0).all()
+            buf = torch.full((n * 243 + 8,), -7.0, dtype=torch.bfloat16, device="cuda")
+            engine.game_gather_planes(st[:n], out=buf[off:off + n * 243])
+            b = buf.float().cpu().numpy()
+            assert (b[off:off + n * 243].reshape(n, 243) == ref_chw[:n]).all()
+            assert (b[:off] == -7.0).all() and (b[off + n * 243:] == -7.0).all()
+    # aligned destination: nothing written past the end either
+    n = 257
+    buf = torch.full((n * 243 + 16,), -7.0, dtype=torch.float32, device="cuda")
+    engine.game_encode(st[:n], out=buf[:n * 243])
+    assert (buf[n * 243:].cpu().numpy() == -7.0).all()

@@ -70,11 +70,139 @@ __device__ __forceinline__ uint32_t warp_picture_rows(const PackedState& s, int 
     return (lane < 27) ? picture_row(x, R) : 0u;
 }
 
-// cpp/uttt_game.cpp:244-280: float HWC (9,9,3).  One warp per position: the 32-byte state is loaded once, the legal
-// mask and the 27 picture rows are computed once per warp, every store instruction of the warp writes 128 contiguous
-// bytes.  HBM-bound by design: 32 B in, 972 B out per position.
-__global__ void __launch_bounds__(256) encode_kernel(const PackedState* __restrict__ in, float* __restrict__ planes,
-                                                     int64_t n) {
+// ---- encode / gather: bit string per block, 16-byte stores ----
+// A position's planes are 243 cells that are 0 or 1, i.e. a 243-bit string; a block of PLANES_POS positions owns one
+// contiguous, 16-byte aligned slice of the output.  Phase 1 (thread per position): build the position's bit string
+// in output element order from the bitboards with word-parallel bit permutations and OR it into the block's
+// string in shared memory at bit 243*t.  Phase 2 (all threads, position boundaries forgotten): every 16-byte output
+// vector is a 4-bit (fp32) or 8-bit (bf16) slice of the string, expanded through a 16-entry table.  HBM traffic is
+// the algorithmic 32 B in + 972 B (fp32 HWC) or 486 B (bf16 CHW) out per position.
+constexpr int PLANES_POS = 256;                                  // positions per block
+constexpr int PLANES_WORDS = (PLANES_POS * 243 + 31) / 32 + 8;   // block bit string (+ spill of the last position)
+
+// 27-bit word of 3 sub-boards x 9 cells  ->  3 picture rows x 9 columns: transposes the 3x3 grid of 3-bit groups
+__device__ __forceinline__ uint32_t rows27(uint32_t w) {
+    uint32_t t = ((w >> 6) ^ w) & 0x00038038u;      // groups (board 0,row 1)<->(1,0) and (1,2)<->(2,1)
+    w ^= t | (t << 6);
+    t = ((w >> 12) ^ w) & 0x000001C0u;              // groups (0,2)<->(2,0)
+    w ^= t | (t << 12);
+    return w;
+}
+// bit i -> bit 3i for a 9-bit value
+__device__ __forceinline__ uint32_t spread9x3(uint32_t x) {
+    x = (x | (x << 16)) & 0x030000FFu;
+    x = (x | (x << 8)) & 0x0300F00Fu;
+    x = (x | (x << 4)) & 0x030C30C3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+// nine 27-bit chunks at bit 27*m -> the block string at bit 243*t
+__device__ __forceinline__ void or_position_bits(uint32_t* S, const uint32_t chunk[9], int t) {
+    uint32_t W[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) W[k] = 0u;
+#pragma unroll
+    for (int m = 0; m < 9; m++) {
+        const int off = 27 * m, k = off >> 5, sh = off & 31;
+        W[k] |= chunk[m] << sh;
+        if (sh > 5) W[k + 1] |= chunk[m] >> (32 - sh);
+    }
+    int bit0 = 243 * t, b = bit0 >> 5, o = bit0 & 31;
+#pragma unroll
+    for (int k = 0; k <= 8; k++) {
+        uint32_t hi = (k < 8) ? W[k] : 0u, lo = (k > 0) ? W[k - 1] : 0u;
+        uint32_t v = __funnelshift_l(lo, hi, o);
+        if (v) atomicOr(S + b + k, v);
+    }
+}
+
+template <bool HWC>
+__device__ __forceinline__ void position_chunks(const PackedState& s, uint32_t chunk[9]) {
+    uint32_t lm[3];
+    legal_mask(s, lm);
+    if (HWC) {          // element (R*9 + C)*3 + plane: chunk R = the three planes' rows R interleaved bit by bit
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            uint32_t a = rows27(s.w[j]), b = rows27(s.w[3 + j]), c = rows27(lm[j]);
+#pragma unroll
+            for (int sr = 0; sr < 3; sr++)
+                chunk[3 * j + sr] = spread9x3((a >> (9 * sr)) & 0x1FFu) | (spread9x3((b >> (9 * sr)) & 0x1FFu) << 1) |
+                                    (spread9x3((c >> (9 * sr)) & 0x1FFu) << 2);
+        }
+    } else {            // element plane*81 + R*9 + C: chunk 3*plane + j = picture rows 3j..3j+2 of the plane
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            chunk[j] = rows27(s.w[j]);
+            chunk[3 + j] = rows27(s.w[3 + j]);
+            chunk[6 + j] = rows27(lm[j]);
+        }
+    }
+}
+
+template <bool HWC>
+__device__ __forceinline__ void block_bit_string(uint32_t* S, const PackedState* __restrict__ in, int64_t pos0,
+                                                 int npos) {
+    for (int k = threadIdx.x; k < PLANES_WORDS; k += blockDim.x) S[k] = 0u;
+    __syncthreads();
+    if ((int)threadIdx.x < npos) {
+        uint32_t chunk[9];
+        position_chunks<HWC>(load_state(in + pos0 + threadIdx.x), chunk);
+        or_position_bits(S, chunk, threadIdx.x);
+    }
+    __syncthreads();
+}
+
+// cpp/uttt_game.cpp:244-280: float HWC (9,9,3)
+__global__ void __launch_bounds__(PLANES_POS) encode_kernel(const PackedState* __restrict__ in,
+                                                            float* __restrict__ planes, int64_t n) {
+    __shared__ uint32_t S[PLANES_WORDS];
+    __shared__ float4 lut[16];
+    if (threadIdx.x < 16) {
+        int v = threadIdx.x;
+        lut[v] = make_float4((float)(v & 1), (float)((v >> 1) & 1), (float)((v >> 2) & 1), (float)((v >> 3) & 1));
+    }
+    int64_t pos0 = (int64_t)blockIdx.x * PLANES_POS;
+    int npos = (int)min((int64_t)PLANES_POS, n - pos0);
+    block_bit_string<true>(S, in, pos0, npos);
+    float* out = planes + pos0 * 243;
+    int total = npos * 243, nvec = total >> 2;
+    float4* out4 = reinterpret_cast<float4*>(out);
+    for (int q = threadIdx.x; q < nvec; q += PLANES_POS) out4[q] = lut[(S[q >> 3] >> ((q & 7) * 4)) & 15u];
+    int e = 4 * nvec + threadIdx.x;
+    if (e < total) out[e] = (float)((S[e >> 5] >> (e & 31)) & 1u);
+}
+
+// leaf gather (pv_mcts_cpp.py:47-60): bf16 CHW (3,9,9) rows of the network's input batch
+__global__ void __launch_bounds__(PLANES_POS) gather_planes_kernel(const PackedState* __restrict__ in,
+                                                                   __nv_bfloat16* __restrict__ planes, int64_t n) {
+    __shared__ uint32_t S[PLANES_WORDS];
+    __shared__ uint2 lut[16];
+    if (threadIdx.x < 16) {
+        uint32_t v = threadIdx.x;
+        lut[v] = make_uint2(((v & 1u) ? 0x3F80u : 0u) | ((v & 2u) ? 0x3F800000u : 0u),
+                            ((v & 4u) ? 0x3F80u : 0u) | ((v & 8u) ? 0x3F800000u : 0u));
+    }
+    int64_t pos0 = (int64_t)blockIdx.x * PLANES_POS;
+    int npos = (int)min((int64_t)PLANES_POS, n - pos0);
+    block_bit_string<false>(S, in, pos0, npos);
+    __nv_bfloat16* out = planes + pos0 * 243;
+    int total = npos * 243, nvec = total >> 3;
+    uint4* out4 = reinterpret_cast<uint4*>(out);
+    for (int q = threadIdx.x; q < nvec; q += PLANES_POS) {
+        uint32_t byte = (S[q >> 2] >> ((q & 3) * 8)) & 255u;
+        uint2 lo = lut[byte & 15u], hi = lut[byte >> 4];
+        out4[q] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+    int e = 8 * nvec + threadIdx.x;
+    if (e < total)
+        out[e] = __ushort_as_bfloat16(((S[e >> 5] >> (e & 31)) & 1u) ? (unsigned short)0x3F80 : (unsigned short)0);
+}
+
+// Same outputs for a destination that is not 16-byte aligned (a caller's sub-view): one warp per position, 4-byte /
+// 2-byte stores, every store instruction of the warp contiguous.
+__global__ void __launch_bounds__(256) encode_unaligned_kernel(const PackedState* __restrict__ in,
+                                                               float* __restrict__ planes, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (i >= n) return;
@@ -89,11 +217,8 @@ __global__ void __launch_bounds__(256) encode_kernel(const PackedState* __restri
         if (e < 243) out[e] = (float)((m >> C) & 1u);
     }
 }
-
-// leaf gather (pv_mcts_cpp.py:47-60): bf16 CHW (3,9,9) rows of the network's input batch; same warp-per-position
-// scheme, 32 B in, 486 B out per position.
-__global__ void __launch_bounds__(256) gather_planes_kernel(const PackedState* __restrict__ in,
-                                                            __nv_bfloat16* __restrict__ planes, int64_t n) {
+__global__ void __launch_bounds__(256) gather_planes_unaligned_kernel(const PackedState* __restrict__ in,
+                                                                      __nv_bfloat16* __restrict__ planes, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (i >= n) return;
@@ -280,15 +405,23 @@ int uttt_game_legal_mask(const uint32_t* states, uint32_t* masks, uint8_t* statu
 
 int uttt_game_encode(const uint32_t* states, float* planes, int64_t n, void* stream) {
     if (n <= 0) return 0;
-    encode_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>((const PackedState*)states, planes, n);
+    if (((uintptr_t)planes & 15u) == 0)
+        encode_kernel<<<ceil_div(n, PLANES_POS), PLANES_POS, 0, (cudaStream_t)stream>>>((const PackedState*)states,
+                                                                                          planes, n);
+    else
+        encode_unaligned_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>((const PackedState*)states, planes, n);
     UTTT_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int uttt_game_gather_planes(const uint32_t* states, void* planes, int64_t n, void* stream) {
     if (n <= 0) return 0;
-    gather_planes_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(
-        (const PackedState*)states, (__nv_bfloat16*)planes, n);
+    if (((uintptr_t)planes & 15u) == 0)
+        gather_planes_kernel<<<ceil_div(n, PLANES_POS), PLANES_POS, 0, (cudaStream_t)stream>>>(
+            (const PackedState*)states, (__nv_bfloat16*)planes, n);
+    else
+        gather_planes_unaligned_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(
+            (const PackedState*)states, (__nv_bfloat16*)planes, n);
     UTTT_CUDA_OK(cudaGetLastError());
     return 0;
 }

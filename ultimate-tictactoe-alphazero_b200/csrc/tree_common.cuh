@@ -41,6 +41,24 @@ __device__ __forceinline__ void warp_store_state(PackedState* p, const PackedSta
     if (lane < 8) reinterpret_cast<uint32_t*>(p)[lane] = x;
 }
 
+// fused leaf gather: bf16 CHW (3,9,9) planes of `st` (cpp/uttt_game.cpp:244-280 after the NHWC->NCHW transpose of
+// pv_mcts_cpp.py:60).  Lane 9*plane + R builds the 9-bit picture row R of plane (mover, opponent, legal); every
+// element is then one shuffle + shift, and each store instruction of the warp writes 64 contiguous bytes.
+__device__ __forceinline__ void warp_write_planes(__nv_bfloat16* pl, const PackedState& st, const uint32_t lm[3], int lane) {
+    int plane = lane / 9, R = lane - 9 * plane;
+    uint32_t x[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) x[j] = (plane == 0) ? st.w[j] : (plane == 1 ? st.w[3 + j] : lm[j]);
+    uint32_t rows = (lane < 27) ? picture_row(x, R) : 0u;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int e = lane + 32 * k;
+        int row = e / 9, C = e - 9 * row;
+        uint32_t m = __shfl_sync(FULL, rows, row & 31);
+        if (e < 243) pl[e] = __ushort_as_bfloat16(((m >> C) & 1u) ? (unsigned short)0x3F80 : (unsigned short)0);
+    }
+}
+
 // Philox temperature-1 sampling over the root visit counts; returns the chosen action.
 __device__ __forceinline__ int sample_move(const TreeParams& P, const TreeView& T, const TreeCtl& c, const uint32_t lm[3], int lane) {
     int L = c.n_root;

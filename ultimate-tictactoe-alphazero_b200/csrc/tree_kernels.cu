@@ -296,13 +296,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
         warp_store_state(P.nn_states + row, st, lane);
         warp_store_state(P.leaf_state + t, st, lane);
         if (lane == 0) { P.nn_tree[row] = t; P.nn_k[row] = k; }
-        __nv_bfloat16* pl = P.nn_planes + (size_t)row * 243;
-        for (int e = lane; e < 243; e += 32) {
-            int ch = e / 81, cell = e - 81 * ch;
-            int a = action_of_rc(cell / 9, cell % 9);
-            bool v = (ch == 0) ? stone_me(st, a) : (ch == 1 ? stone_opp(st, a) : legal_bit(lm, a));
-            pl[e] = __float2bfloat16(v ? 1.0f : 0.0f);
-        }
+        warp_write_planes(P.nn_planes + (size_t)row * 243, st, lm, lane);
         c.phase = PHASE_PENDING;
         c.pend_k = k;
         c.nn_row = row;

@@ -142,13 +142,7 @@ __device__ __forceinline__ int tp_queue_leaf(const TreeParams& P, int t, const P
     row = __shfl_sync(FULL, row, 0);
     warp_store_state(P.nn_states + row, st, lane);
     if (lane == 0) { P.nn_tree[row] = t; P.nn_k[row] = 1; }
-    __nv_bfloat16* pl = P.nn_planes + (size_t)row * 243;
-    for (int e = lane; e < 243; e += 32) {
-        int ch = e / 81, cell = e - 81 * ch;
-        int a = action_of_rc(cell / 9, cell % 9);
-        bool v = (ch == 0) ? stone_me(st, a) : (ch == 1 ? stone_opp(st, a) : legal_bit(lm, a));
-        pl[e] = __float2bfloat16(v ? 1.0f : 0.0f);
-    }
+    warp_write_planes(P.nn_planes + (size_t)row * 243, st, lm, lane);
     return row;
 }
 

@@ -134,20 +134,22 @@ def game_legal_mask(states, stream=None):
     return masks, status
 
 
-def game_encode(states, stream=None):
-    """-> float32 (n,9,9,3) HWC planes exactly like State.to_input_tensor (cpp/uttt_game.cpp:244-280)"""
+def game_encode(states, stream=None, out=None):
+    """-> float32 (n,9,9,3) HWC planes exactly like State.to_input_tensor (cpp/uttt_game.cpp:244-280);
+    `out`: optional contiguous float32 destination of n*243 elements (any 4-byte alignment)"""
     import torch
     n = states.shape[0]
-    planes = torch.empty((n, 9, 9, 3), dtype=torch.float32, device=states.device)
+    planes = torch.empty((n, 9, 9, 3), dtype=torch.float32, device=states.device) if out is None else out
     _check(load_library().uttt_game_encode(_ptr(states), _ptr(planes), n, _stream(stream)))
     return planes
 
 
-def game_gather_planes(states, stream=None):
-    """-> bfloat16 (n,3,9,9) network input batch (pv_mcts_cpp.py:47-60)"""
+def game_gather_planes(states, stream=None, out=None):
+    """-> bfloat16 (n,3,9,9) network input batch (pv_mcts_cpp.py:47-60);
+    `out`: optional contiguous bfloat16 destination of n*243 elements (any 2-byte alignment)"""
     import torch
     n = states.shape[0]
-    planes = torch.empty((n, 3, 9, 9), dtype=torch.bfloat16, device=states.device)
+    planes = torch.empty((n, 3, 9, 9), dtype=torch.bfloat16, device=states.device) if out is None else out
     _check(load_library().uttt_game_gather_planes(_ptr(states), _ptr(planes), n, _stream(stream)))
     return planes
 
