@@ -114,7 +114,7 @@ struct NetWeights {
     float* conv_in_b;     // [128]
     float* res_w;         // [32][9][128][128]
     float* res_b;         // [32][128]
-    // bf16 tensor-core path: [layer][tap][k-panel 16][cout 128][8]  (UMMA canonical K-major, no swizzle)
+    // bf16 tensor-core path: [layer][72 K-blocks, tcx::kblock_of][2 k-panels][cout 128][8]  (UMMA canonical K-major, no swizzle)
     __nv_bfloat16* res_w_bf16;
     __nv_bfloat16* conv_in_w_bf16;   // conv_input as a K=16-per-tap tensor-core layer: [12 taps (9 used)][2][128][8]
     float* bias_all;                 // [33][128]: conv_input shift followed by the 32 trunk layers' shifts

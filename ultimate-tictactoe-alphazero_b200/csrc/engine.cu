@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 using namespace uttt;
 
@@ -46,7 +47,9 @@ __global__ void __launch_bounds__(256) pack_res_kernel(const float* __restrict__
     float sc = __fdiv_rn(g, __fsqrt_rn(__fadd_rn(v, 1e-5f)));
     float val = __fmul_rn(raw[i], sc);
     w32[(((size_t)l * 9 + tap) * 128 + ci) * 128 + co] = val;
-    w16[((((size_t)l * 9 + tap) * 16 + ci / 8) * 128 + co) * 8 + (ci % 8)] = __float2bfloat16(val);
+    // tensor-core copy: 72 K-blocks per layer in the order of tcx::kblock_of, each [2 panels][128 co][8 ci]
+    int blk = tcx::kblock_of(tap, ci / 16);
+    w16[((((size_t)l * 72 + blk) * 2 + ((ci / 8) & 1)) * 128 + co) * 8 + (ci % 8)] = __float2bfloat16(val);
     if (ci == 0 && tap == 0) b32[l * 128 + co] = __fsub_rn(beta, __fmul_rn(m, sc));
 }
 

@@ -13,7 +13,7 @@
 //     (SBO = 128 B between 8-row groups, LBO = panel stride between the two K halves).
 //   * B operand (weights, bf16, BN scale folded): pre-packed in HBM in exactly the shared-memory
 //     image [layer][tap][ci/8][co][ci%8]; streamed by one elected thread with bulk async copies
-//     (cp.async.bulk -> UBLKCP, mbarrier complete_tx) through a 5-stage ring of 16 KiB half-taps.
+//     (cp.async.bulk -> UBLKCP, mbarrier complete_tx) through a 5-stage ring of 16 KiB stages (4 K-blocks).
 //     Each stage feeds 16 MMAs (4 tiles x 4 K-steps), i.e. weights are re-used across the 4 tiles.
 //   * D accumulators: 4 x (128 lanes x 128 fp32 columns) = all 512 TMEM columns.
 //   * Epilogue (16 warps, one TMEM lane quarter of one tile each): tcgen05.ld -> +shift (+skip)
@@ -56,7 +56,7 @@ constexpr uint32_t TC_IDESC = tcx::IDESC_M128_N128_BF16;
 using namespace tcx;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
+trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2][128][8] bf16
                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
                 const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
                 const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
@@ -301,12 +301,13 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] b
                                 }
                             }
                         } else {
-                            const int tap = (s - 1) >> 1, half = (s - 1) & 1;
-                            const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
-                            const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * TC_PANEL_BYTES;
+                            // stage s holds K-blocks 4(s-1) .. 4(s-1)+3 in the order of tcx::kblock_of
 #pragma unroll
                             for (int ks = 0; ks < 4; ks++) {
-                                umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * TC_PANEL_BYTES, TC_PANEL_BYTES, 128),
+                                int q, tap, unit;
+                                kblock_decode(4 * (s - 1) + ks, q, tap, unit);
+                                const uint32_t a0 = a_tile + (uint32_t)(tap_shift(tap) * 16) + (uint32_t)(2 * unit) * TC_PANEL_BYTES;
+                                umma_bf16(tmem_d, make_desc(a0, TC_PANEL_BYTES, 128),
                                           make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), TC_IDESC, 1u);
                             }
                         }

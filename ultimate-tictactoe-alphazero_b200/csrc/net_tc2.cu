@@ -21,6 +21,19 @@
 // instruction-latency bound, so it wants warps, not wider threads), 16 weight producer, 17-18 MMA issuers.
 #include "tc_common.cuh"
 
+//#define UTTT_TC2_DETAIL 1
+#ifdef UTTT_TC2_DETAIL
+#define DBG_ROW(l) ((l) & 15)          // the detail stamps use rows 16..31
+#else
+#define DBG_ROW(l) (l)
+#endif
+#ifndef UTTT_TC2_NQ
+#define UTTT_TC2_NQ 4
+#endif
+#ifndef UTTT_TC2_NBUF
+#define UTTT_TC2_NBUF 2
+#endif
+
 namespace uttt {
 namespace tc2 {
 
@@ -44,20 +57,25 @@ struct Cfg {
     static constexpr int PANEL_BYTES = AROWS * 16;
     static constexpr int A_BYTES = 18 * PANEL_BYTES;      // 16 channel panels + the constant panel pair of the bias MMA
     static constexpr int STAGES = (LT == 2) ? 8 : 6;
+    // LT = 2 has TMEM for two accumulators per tile (4 x 128 = 512 columns): the layers alternate between them, and the
+    // epilogue publishes its output per 16-column chunk (NQ act_ready barriers per tile), so the MMAs of layer L+1
+    // run while the epilogue of layer L is still converting the other chunks.
+    static constexpr int NQ = (LT == 2) ? UTTT_TC2_NQ : 1;
+    static constexpr int NBUF = (LT == 2) ? UTTT_TC2_NBUF : 1;
     static constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
     static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [128*LT rows][4] floats: head partial sums
     static constexpr int SMEM_BYTES = HEAD_OFF + 128 * LT * 16;
     static constexpr int EPI_WARPS = 8 * LT;         // (tile, lane quarter, column half)
     static constexpr int THREADS = (EPI_WARPS + 1 + LT) * 32;
     static constexpr int SKIP_ROWS = 128 * LT;
-    static constexpr uint32_t TMEM_COLS = (LT == 2) ? 256u : 512u;
+    static constexpr uint32_t TMEM_COLS = 512u;
 };
 
 using namespace tcx;
 
 template <int LT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<LT>::THREADS, 1)
-trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] bf16
+trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2][128][8] bf16
                  const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
                  const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
                  const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
@@ -70,7 +88,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
     using C = Cfg<LT>;
     constexpr int LOC_TILES = C::LOC_TILES, MAX_P = C::MAX_P, PANEL_BYTES = C::PANEL_BYTES, A_BYTES = C::A_BYTES,
                   STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS,
-                  SKIP_ROWS = C::SKIP_ROWS;
+                  SKIP_ROWS = C::SKIP_ROWS, NQ = C::NQ, NBUF = C::NBUF;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
@@ -93,10 +111,11 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
     const uint32_t sA_u = smem_u32(sA);
     const uint32_t sB_u = sA_u + A_BYTES;
     const uint32_t bar_u = sA_u + BAR_OFF;
-    // barriers: full[STAGES], empty[STAGES], accum[LT], act[LT], bnd_accum; then the tmem base holder
+    // barriers: full[STAGES], empty[STAGES], accum[LT], act[LT][NQ], bnd_accum; then the tmem base holder
     const uint32_t bar_full = bar_u, bar_empty = bar_u + 8 * STAGES, bar_accum = bar_u + 16 * STAGES,
-                   bar_act = bar_accum + 8 * LOC_TILES, bar_bnd = bar_act + 8 * LOC_TILES;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * STAGES + 16 * LOC_TILES + 8);
+                   bar_act = bar_accum + 8 * LOC_TILES, bar_bnd = bar_act + 8 * LOC_TILES * NQ;
+    static_assert(16 * STAGES + 8 * LOC_TILES * (1 + NQ) + 8 + 4 <= 256, "barrier block");
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * STAGES + 8 * LOC_TILES * (1 + NQ) + 8);
     // the tile of this CTA that touches the peer's rows, and the quarter-warp that owns the shared rows
     const int bnd_tile = (rank == 0) ? tiles - 1 : 0;
     const int bnd_quarter = (rank == 0) ? 3 : 0;
@@ -105,8 +124,8 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
         for (int i = 0; i < STAGES; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, tiles > 0 ? tiles : 1); }
         for (int t = 0; t < LOC_TILES; t++) {
             mbar_init(bar_accum + 8 * t, 1);
-            int c = 8 + (t > 0 ? 2 : 0) + (t < tiles - 1 ? 2 : 0) + ((has_peer && t == bnd_tile) ? 2 : 0);
-            mbar_init(bar_act + 8 * t, c);
+            int c = 8 + (t > 0 ? 2 : 0) + (t < tiles - 1 ? 2 : 0);      // (the peer's halo rows arrive as transaction bytes)
+            for (int q = 0; q < NQ; q++) mbar_init(bar_act + 8 * (t * NQ + q), c);
         }
         mbar_init(bar_bnd, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -152,12 +171,27 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
             const bool nb_lo = (quarter == 0) && (lt > 0);
             const bool nb_hi = (quarter == 3) && (lt < tiles - 1);
             const bool bnd = has_peer && (lt == bnd_tile) && (quarter == bnd_quarter);
-            // rows this thread mirrors into the peer's margin: rank 0 lanes 21..31 -> peer lead rows 0..10,
-            // rank 1 lanes 0..10 -> peer tail rows (LEAD + 128*T0 + lane)
-            const bool mirror = bnd && ((rank == 0) ? (lane >= 21) : (lane < 11));
-            const uint32_t peer_row = (rank == 0) ? (uint32_t)(lane - 21) : (uint32_t)(LEAD + 128 * T0 + lane);
-            const uint32_t peer_srow = map_to_rank(sA_u + (uint32_t)(chalf * 8) * PANEL_BYTES + peer_row * 16u, peer);
-            const uint32_t peer_act = map_to_rank(bar_act + 8 * ((rank == 0) ? 0 : (T0 - 1)), peer);
+            // The 11 boundary rows of this CTA (rank 0: its last rows -> the peer's lead margin, rank 1: its first rows ->
+            // the peer's tail margin) are pushed panel by panel with bulk shared->shared copies that count their bytes on
+            // the peer's act_ready barrier; the peer's chalf-0 boundary warp announces them with expect_tx.
+            constexpr uint32_t HALO_BYTES = 11 * 16;
+            const uint32_t halo_src = sA_u + (uint32_t)(chalf * 8) * PANEL_BYTES +
+                                      (uint32_t)(LEAD + ((rank == 0) ? (128 * tiles - 11) : 0)) * 16u;
+            const uint32_t halo_dst = map_to_rank(sA_u + (uint32_t)(chalf * 8) * PANEL_BYTES +
+                                                  (uint32_t)((rank == 0) ? 0 : (LEAD + 128 * T0)) * 16u, peer);
+            const uint32_t peer_act = map_to_rank(bar_act + 8 * NQ * ((rank == 0) ? 0 : (T0 - 1)), peer);
+            // publish rows of this warp (chunk barrier q of its tile and of the row neighbours); `tx` = bytes the peer
+            // pushes into this CTA's margin for the same barrier phase
+            auto publish = [&](int q, uint32_t tx) {
+                if (bnd && chalf == 0) mbar_expect_tx(bar_act + 8 * (lt * NQ + q), tx);
+                else mbar_arrive(bar_act + 8 * (lt * NQ + q));
+                if (nb_lo) mbar_arrive(bar_act + 8 * ((lt - 1) * NQ + q));
+                if (nb_hi) mbar_arrive(bar_act + 8 * ((lt + 1) * NQ + q));
+            };
+            auto push_halo = [&](int panel, int q) {       // panel relative to this warp's column half
+                bulk_s2peer(halo_dst + (uint32_t)panel * PANEL_BYTES, halo_src + (uint32_t)panel * PANEL_BYTES, HALO_BYTES,
+                            peer_act + 8u * (uint32_t)q);
+            };
             const uint4 zero4 = make_uint4(0, 0, 0, 0);
 
             // prologue: the three input planes of this row go into channel panel 0 (channels 3..15 are zero): the
@@ -172,15 +206,15 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 }
                 uint8_t* dst = sA + (size_t)chalf * PANEL_BYTES + (size_t)(LEAD + lr) * 16;
                 *reinterpret_cast<uint4*>(dst) = pk;
-                if (mirror) st_cluster_v4(map_to_rank(sA_u + (uint32_t)chalf * PANEL_BYTES + peer_row * 16u, peer), pk);
             }
-            fence_async_all();
+            fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-                mbar_arrive(bar_act + 8 * lt);
-                if (nb_lo) mbar_arrive(bar_act + 8 * (lt - 1));
-                if (nb_hi) mbar_arrive(bar_act + 8 * (lt + 1));
-                if (bnd) mbar_arrive_remote(peer_act);
+#pragma unroll
+                for (int q = 0; q < NQ; q++) publish(q, q == 0 ? 2 * HALO_BYTES : 0u);
+                // input panel `chalf` of the boundary rows (halo_src / halo_dst point at panel 8*chalf)
+                if (bnd) bulk_s2peer(halo_dst - (uint32_t)(chalf * 7) * PANEL_BYTES, halo_src - (uint32_t)(chalf * 7) * PANEL_BYTES,
+                                     HALO_BYTES, peer_act);
             }
 
             // the last layer (heads' 1x1 convs instead of a write-back) is a separate instantiation of the body so that
@@ -189,6 +223,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
             auto epilogue_layer = [&](auto last_tag) {
                 constexpr bool last = decltype(last_tag)::value;
                 const uint32_t lpar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
+                const uint32_t tsrc = taddr + ((NBUF == 2) ? lpar * (uint32_t)(LOC_TILES * 128) : 0u);   // this layer's accumulator
                 const bool second = (layer >= 0) && (layer & 1) != 0;   // conv2 of a block: add the skip connection
                 const bool keep = second || (layer < 0);                // output is the input of the next block: keep it as skip
                 // the skip connection (8 x 16 B per thread) is fetched from L2 while the MMAs still run
@@ -198,20 +233,23 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 uint4 sk[SKP];
 #pragma unroll
                 for (int j = 0; j < SKP; j++) sk[j] = (second && valid) ? srow_skip[(size_t)j * SKIP_ROWS] : zero4;
-                mbar_wait(bar_accum + 8 * lt, lpar, 32);
-                if (nb_lo) mbar_wait(bar_accum + 8 * (lt - 1), lpar, 32);
-                if (nb_hi) mbar_wait(bar_accum + 8 * (lt + 1), lpar, 32);
-                if (bnd) mbar_wait<true>(bar_bnd, lpar, 32);     // the peer's boundary-tile MMAs have retired
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
+                mbar_wait_spin<false>(bar_accum + 8 * lt, lpar);
+                if (nb_lo) mbar_wait_spin<false>(bar_accum + 8 * (lt - 1), lpar);
+                if (nb_hi) mbar_wait_spin<false>(bar_accum + 8 * (lt + 1), lpar);
+                if (bnd) mbar_wait_spin<false>(bar_bnd, lpar);    // the peer's boundary-tile MMAs have retired
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[DBG_ROW(layer) * 4 + 2] = clock64();
                 tc_fence_after();
+#ifdef UTTT_TC2_DETAIL
+                if (dbg && blockIdx.x == 0 && iter == 0 && lane == 0 && layer == 4) dbg[96 + warp] = clock64();
+#endif
                 float va[16], vb[16];
                 float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
-                tmem_ld16(taddr, va);
+                tmem_ld16(tsrc, va);
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
                     float* v = (ch & 1) ? vb : va;
                     tmem_ld_wait();
-                    if (ch < 3) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
+                    if (ch < 3) tmem_ld16(tsrc + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
                     f16x8_add2(sk[(2 * ch) % SKP], v);
                     f16x8_add2(sk[(2 * ch + 1) % SKP], v + 8);
                     if (SKP == 4 && ch < 2 && second && valid) {     // refill the two registers just consumed: panels +4
@@ -234,22 +272,32 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                         for (int j = 0; j < 2; j++) {
                             uint4 pk = valid ? relu_pack8_bf16(v + 8 * j) : zero4;      // padding rows stay zero
                             *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = pk;
-                            if (mirror) st_cluster_v4(peer_srow + (uint32_t)(ch * 2 + j) * PANEL_BYTES, pk);
                             if (keep && valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = relu_pack8_f16(v + 8 * j);
+                        }
+                        if (NQ == 4 || ch == 3) {        // channels 16(4*chalf + ch) .. +15 of these rows are in place
+                            fence_async_smem();
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) {
+                                if (NQ == 4) {
+                                    publish(ch, 4 * HALO_BYTES);
+                                    if (bnd) { push_halo(2 * ch, ch); push_halo(2 * ch + 1, ch); }
+                                } else {
+                                    publish(0, 16 * HALO_BYTES);
+                                    if (bnd) {
+#pragma unroll
+                                        for (int pnl = 0; pnl < 8; pnl++) push_halo(pnl, 0);
+                                    }
+                                }
+                            }
+#ifdef UTTT_TC2_DETAIL
+                            if (dbg && blockIdx.x == 0 && iter == 0 && lane == 0 && layer == 4 && ch == 0) dbg[64 + warp] = clock64();
+                            if (dbg && blockIdx.x == 0 && iter == 0 && lane == 0 && layer == 4 && ch == 3) dbg[80 + warp] = clock64();
+#endif
                         }
                     }
                 }
-                if constexpr (!last) {
-                    fence_async_all();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(bar_act + 8 * lt);
-                        if (nb_lo) mbar_arrive(bar_act + 8 * (lt - 1));
-                        if (nb_hi) mbar_arrive(bar_act + 8 * (lt + 1));
-                        if (bnd) mbar_arrive_remote(peer_act);
-                    }
-                } else {
+                if constexpr (last) {
                     // combine the two column halves of the row (two warps) and emit BN shift + ReLU of the head convs
                     if (chalf == 1) *hscr = make_float4(h0, h1, h2, 0.0f);
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + lt * 4 + quarter) : "memory");
@@ -260,7 +308,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                         hrow[162] = fmaxf(h2 + o.z + __ldg(headw + 386), 0.0f);
                     }
                 }
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 3] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[DBG_ROW(layer) * 4 + 3] = clock64();
             };
 #pragma unroll 1
             for (layer = -1; layer < NET_LAYERS - 1; layer++) epilogue_layer(std::false_type{});
@@ -292,68 +340,111 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][9][16][128][8] 
                 }
             }
         } else {
-            // ================= MMA issuers: warp 9+t drives local accumulator tile t =================
+            // ================= MMA issuers: warp EPI_WARPS+1+t drives local accumulator tile t =================
+            // One thread issues every MMA of a tile, and two tiles share the tensor pipe: the issuer has 128 cycles per
+            // MMA before it becomes the bottleneck.  Its loop is therefore unrolled over the 18 weight stages of a layer
+            // (all K-block offsets are immediates), keeps stage / parity as running counters and waits without back-off.
             const int lt = warp - (EPI_WARPS + 1);
             if (lt >= tiles) continue;
             const bool leader = elect_one();
-            const uint32_t tmem_d = tmem_base + (uint32_t)(lt * 128);
             const uint32_t a_tile = sA_u + (uint32_t)(LEAD + lt * 128) * 16u;
             const bool signal_peer = has_peer && (lt == bnd_tile);
+            const uint64_t a_desc = make_desc(a_tile, PANEL_BYTES, 128);         // + (row shift + panel offset) / 16: shared
+            const uint64_t b_desc = make_desc(sB_u, 2048, 128);                  //   addresses are < 256 KiB, no carry
+            const uint64_t bias_a = a_desc + (uint64_t)(16u * PANEL_BYTES / 16u);
+            int gn = iter * GROUP_STAGES;
+            int stage = gn % STAGES;
+            uint32_t par = (uint32_t)((gn / STAGES) & 1);
+            uint64_t b_st = 0;
+            // rows of chunk q are in place (own warps, row neighbours, and across the cluster for the boundary tile)
+            auto wait_act = [&](int q, uint32_t apar) {
+                mbar_wait_spin<false>(bar_act + 8 * (lt * NQ + q), apar);
+                tc_fence_after();
+            };
+            auto next_stage = [&]() {              // waits for the next weight stage; b_st = descriptor of its first block
+                mbar_wait_spin<false>(bar_full + 8 * stage, par);
+                tc_fence_after();
+                b_st = b_desc + (uint64_t)(uint32_t)(stage * (STAGE_BYTES / 16));
+            };
+            auto release_stage = [&]() {           // leader only: frees the stage when the MMAs issued so far retire
+                umma_commit(bar_empty + 8 * stage);
+            };
+            auto advance = [&]() {
+                if (++stage == STAGES) { stage = 0; par ^= 1u; }
+            };
 #pragma unroll 1
             for (int layer = -1; layer < NET_LAYERS; layer++) {
                 const uint32_t apar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
-                if (signal_peer) mbar_wait<true>(bar_act + 8 * lt, apar, 0);
-                else mbar_wait(bar_act + 8 * lt, apar, 0);
-                fence_async_all();
-                tc_fence_after();
-                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0) dbg[layer * 4 + 0] = clock64();
-                const int n_st = 1 + ((layer < 0) ? IN_STAGES : STAGES_PER_LAYER);
-                const int st0 = iter * GROUP_STAGES +
-                                ((layer < 0) ? 0 : (IN_STAGES + 1) + layer * (STAGES_PER_LAYER + 1));
-#pragma unroll 1
-                for (int s = 0; s < n_st; s++) {
-                    const int gn = st0 + s;
-                    const int stage = gn % STAGES;
-                    const uint32_t par = (uint32_t)((gn / STAGES) & 1);
-                    mbar_wait(bar_full + 8 * stage, par);
-                    tc_fence_after();
-                    if (leader) {
-                        const uint32_t b0 = sB_u + (uint32_t)stage * STAGE_BYTES;
-                        if (s == 0) {
-                            // accumulator := BN shift (constant panel x bias block); starts the layer's accumulation
-                            umma_bf16(tmem_d, make_desc(a_tile + 16u * PANEL_BYTES, PANEL_BYTES, 128), make_desc(b0, 2048, 128),
-                                      IDESC, 0u);
-                        } else if (layer < 0) {
-                            // conv_input: block j of stage s is tap 4(s-1)+j, K = 16 (channel panels 0,1)
+                const uint32_t tmem_d = tmem_base + (uint32_t)(lt * 128) + ((NBUF == 2) ? apar * (uint32_t)(LOC_TILES * 128) : 0u);
+                // accumulator := BN shift (constant panel x bias block); starts the layer's accumulation.  With two
+                // accumulators per tile this needs no activation: it is issued while the previous epilogue still runs.
+                if (NQ == 1 || layer < 0) {
+#pragma unroll
+                    for (int q = 0; q < NQ; q++) wait_act(q, apar);
+                    if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0) dbg[DBG_ROW(layer) * 4 + 0] = clock64();
+                }
+                next_stage();
+                if (leader) {
+                    umma_bf16(tmem_d, bias_a, b_st, IDESC, 0u);
+                    release_stage();
+                }
+                advance();
+                if (layer < 0) {
+                    // conv_input: block j of stage s is tap 4s+j, K = 16 (channel panels 0,1)
+#pragma unroll
+                    for (int s = 0; s < IN_STAGES; s++) {
+                        next_stage();
+                        if (leader) {
 #pragma unroll
                             for (int j = 0; j < 4; j++) {
-                                const int tap = 4 * (s - 1) + j;
-                                if (tap < 9) {
-                                    const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
-                                    umma_bf16(tmem_d, make_desc(a_tile + (uint32_t)(shift * 16), PANEL_BYTES, 128),
-                                              make_desc(b0 + (uint32_t)j * 4096u, 2048, 128), IDESC, 1u);
-                                }
+                                const int tap = 4 * s + j;
+                                if (tap < 9)
+                                    umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)((tap / 3 - 1) * 10 + (tap % 3 - 1)),
+                                              b_st + (uint64_t)(j * 256), IDESC, 1u);
                             }
-                        } else {
-                            const int tap = (s - 1) >> 1, half = (s - 1) & 1;
-                            const int shift = (tap / 3 - 1) * 10 + (tap % 3 - 1);
-                            const uint32_t a0 = a_tile + (uint32_t)(shift * 16) + (uint32_t)(half * 8) * PANEL_BYTES;
-#pragma unroll
-                            for (int ks = 0; ks < 4; ks++) {
-                                umma_bf16(tmem_d, make_desc(a0 + (uint32_t)(2 * ks) * PANEL_BYTES, PANEL_BYTES, 128),
-                                          make_desc(b0 + (uint32_t)ks * 4096u, 2048, 128), IDESC, 1u);
+                            release_stage();
+                            if (s == IN_STAGES - 1) {
+                                umma_commit(bar_accum + 8 * lt);
+                                if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
                             }
                         }
-                        umma_commit(bar_empty + 8 * stage);
-                        if (s == n_st - 1) {
-                            umma_commit(bar_accum + 8 * lt);
-                            if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
-                            if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && layer >= 0) dbg[layer * 4 + 1] = clock64();
-                        }
+                        advance();
                     }
-                    __syncwarp();
+                } else {
+                    // stage s holds K-blocks 4s .. 4s+3 in the order of tcx::kblock_of (channel-quarter-major); the first
+                    // block of quarter q waits for the epilogue's q-th chunk of the previous layer
+#pragma unroll
+                    for (int s = 0; s < STAGES_PER_LAYER; s++) {
+                        next_stage();
+#pragma unroll
+                        for (int ks = 0; ks < 4; ks++) {
+                            const int m = 4 * s + ks, q = m / 18, r = m % 18, tap = r >> 1, unit = q + 4 * (r & 1);
+                            if (NQ == 4 && r == 0) {
+#ifdef UTTT_TC2_DETAIL
+                                if (dbg && blockIdx.x == 0 && iter == 0 && leader && layer == 5) dbg[112 + lt * 8 + 2 * q] = clock64();
+#endif
+                                wait_act(q, apar);
+#ifdef UTTT_TC2_DETAIL
+                                if (dbg && blockIdx.x == 0 && iter == 0 && leader && layer == 5) dbg[113 + lt * 8 + 2 * q] = clock64();
+#endif
+                                if (q == 0 && dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[DBG_ROW(layer) * 4 + 0] = clock64();
+                            }
+                            const int off = (tap / 3 - 1) * 10 + (tap % 3 - 1) + 2 * unit * (PANEL_BYTES / 16);
+                            if (leader) umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)off, b_st + (uint64_t)(ks * 256), IDESC, 1u);
+                        }
+                        if (leader) {
+                            release_stage();
+                            if (s == STAGES_PER_LAYER - 1) {
+                                umma_commit(bar_accum + 8 * lt);
+                                if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
+                                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0) dbg[DBG_ROW(layer) * 4 + 1] = clock64();
+                            }
+                        }
+                        advance();
+                    }
                 }
             }
+            __syncwarp();
         }
     }
 

@@ -14,6 +14,20 @@ namespace tcx {
 // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=bf16 (bits 7,10), K-major A and B, N=128, M=128
 constexpr uint32_t IDESC_M128_N128_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
 
+// K order of a 3x3 layer: 72 blocks of K = 16 (one MMA each).  Block m = 18*q + 2*tap + h multiplies tap `tap` of
+// the 16 input channels of unit u = q + 4h (channels 16u .. 16u+15).  The order is channel-quarter-major: an epilogue
+// warp writes units 0..3 (column half 0) or 4..7 (column half 1) in that order, so the blocks of quarter q only need
+// the q-th 16-column chunk of every epilogue warp -- the next layer's MMAs start while the epilogue is still running.
+// The pre-packed weights (pack_res_kernel, engine.cu) are stored in the same order, 4 KiB per block.
+__host__ __device__ __forceinline__ int kblock_of(int tap, int unit) { return 18 * (unit & 3) + 2 * tap + (unit >> 2); }
+__device__ __forceinline__ void kblock_decode(int m, int& q, int& tap, int& unit) {
+    q = m / 18;
+    int r = m - 18 * q;
+    tap = r >> 1;
+    unit = q + 4 * (r & 1);
+}
+__device__ __forceinline__ int tap_shift(int tap) { return (tap / 3 - 1) * 10 + (tap % 3 - 1); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((addr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
@@ -85,13 +99,50 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
         }
     }
 }
+// Polling wait for the waits on the critical path of a layer (issuer <- epilogue chunk, epilogue <- accumulator): a
+// suspended try_wait wakes up about a thousand cycles after the phase completes, test_wait sees it at once.
+template <bool CLUSTER>
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 28); it++) {
+        if (CLUSTER)
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        else
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok)
+                : "r"(bar), "r"(parity)
+                : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// shared memory of this CTA -> shared memory of a CTA of the cluster, by the async proxy; the bytes are counted on the
+// destination CTA's mbarrier (complete_tx), so the receiver's tensor pipe may read them after a plain wait: no
+// cluster-scope release on the sender (ptxas turns that into MEMBAR.ALL.GPU) and no acquire.cluster on the receiver.
+__device__ __forceinline__ void bulk_s2peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_cluster),
+                 "r"(src_cta), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_dsmem() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
