@@ -183,6 +183,10 @@ int uttt_last_run_profile(uttt_engine *e, int kind, double *ms_out, int64_t *lau
  * MMA start, MMA issue done, accumulators ready (epilogue start), epilogue done */
 int uttt_debug_trunk_timeline(uttt_engine *e, int64_t *out128);
 
+/* diagnostics: how many tensor-core trunk launches evaluated n positions, 64 buckets of 16 (bucket 63 = 1008 and
+ * more), accumulated since creation or the last call with reset != 0 */
+int uttt_debug_batch_histogram(uttt_engine *e, int64_t *out64, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

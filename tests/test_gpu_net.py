@@ -247,26 +247,50 @@ def test_fp32_trunk_vs_reference_golden_outputs(setup, golden_dir):
     assert (pb.argmax(1) == g["policy"].argmax(1)).mean() >= 0.9
 
 
-def test_trunk_variant_boundaries_give_identical_rows(setup):
-    """The trunk kernel is chosen on the device from the batch size (CTA pairs with 2 or 3 tiles, or one CTA per group)
-    and the group size from ceil(n / pairs): every boundary of that dispatch must produce the same rows."""
+def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
+    """The trunk kernel is chosen on the device from the batch size (CTA pairs with 2 or 3 tiles per CTA, one CTA per
+    group above 518 positions) and the group size from ceil(n / pairs): every boundary of that dispatch must produce
+    the same rows.  The CTA-pair kernels accumulate every row in the same order: bit-identical."""
     import engine
     e, model, sts = setup
+    big = np.concatenate([sts] * 5)[:1600]
     e2 = engine.Engine(n_slots=800, max_sims=50, max_batch=8, max_games=8)
     try:
         e2.upload_model(model)
-        big = np.concatenate([sts, sts])[:800]
-        ref_p, ref_v = _forward(e2, big, engine.EVAL_NET_BF16)            # one CTA per group (n > 518)
+        ref_p, ref_v = _forward(e2, big[:800], engine.EVAL_NET_BF16)      # one CTA per group (n > 518)
         pair_p, pair_v = _forward(e2, big[:518], engine.EVAL_NET_BF16)    # CTA pairs, 3 tiles per CTA
         # the two families sum the heads' 1x1 convs in a different order (whole row vs two column halves); on the
         # ill-conditioned random-init net (logits up to +-400) that fp32 reordering shows up at the 1e-5 level
         assert np.abs(pair_p - ref_p[:518]).max() < 1e-3 and np.abs(pair_v - ref_v[:518]).max() < 1e-3
         f32_p, _ = _forward(e2, big[:64], engine.EVAL_NET_FP32)
         assert (ref_p[:64].argmax(1) == f32_p.argmax(1)).mean() > 0.9
-        for n in (2, 3, 73, 74, 75, 147, 148, 149, 221, 222, 223, 295, 296, 297, 369, 370, 371, 372, 443, 444, 445,
-                  517, 518, 519, 520, 739, 740, 741, 800):
+        for n in (1, 2, 3, 73, 74, 75, 147, 148, 149, 221, 222, 223, 295, 296, 297, 369, 370, 371, 372, 443, 444, 445,
+                  500, 517, 518, 519, 520, 739, 740, 741, 800):
             p, v = _forward(e2, big[:n], engine.EVAL_NET_BF16)
             rp, rv = (pair_p, pair_v) if n <= 518 else (ref_p, ref_v)
             assert (p == rp[:n]).all() and (v == rv[:n]).all(), n
     finally:
         e2.close()
+    # UTTT_TRUNK=3: two groups of positions in flight per CTA pair above 370 positions (net_pp.cu, experimental: same
+    # rows bit for bit, also when a pair loops over several super-groups); UTTT_TRUNK=1: one CTA per group only
+    monkeypatch.setenv("UTTT_TRUNK", "3")
+    e3 = engine.Engine(n_slots=1600, max_sims=50, max_batch=8, max_games=8)
+    try:
+        e3.upload_model(model)
+        for n in (370, 371, 444, 445, 500, 518, 519, 592, 593, 666, 667, 740, 741, 1111, 1480, 1481, 1600):
+            p, v = _forward(e3, big[:n], engine.EVAL_NET_BF16)
+            m = min(n, 518)
+            assert (p[:m] == pair_p[:m]).all() and (v[:m] == pair_v[:m]).all(), n
+            m = min(n, 800)
+            assert np.abs(p[:m] - ref_p[:m]).max() < 1e-3, n
+    finally:
+        e3.close()
+    monkeypatch.setenv("UTTT_TRUNK", "1")
+    e1 = engine.Engine(n_slots=800, max_sims=50, max_batch=8, max_games=8)
+    try:
+        e1.upload_model(model)
+        for n in (3, 300, 800):
+            p, v = _forward(e1, big[:n], engine.EVAL_NET_BF16)
+            assert (p == ref_p[:n]).all() and (v == ref_v[:n]).all(), n
+    finally:
+        e1.close()

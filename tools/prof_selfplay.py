@@ -34,3 +34,6 @@ for r in range(a.reps):
           % (a.games, st[0], st[2], st[3], dt, st[0] / dt, prof["tree"][0], prof["trunk"][0],
              flop / (prof["trunk"][0] / 1e3) / 1e12 if prof["trunk"][0] else 0, prof["trunk"][0] / max(prof["trunk"][1], 1),
              prof["heads"][0]))
+    h = e.batch_histogram()
+    print("  evaluator batch sizes (positions: launches): " +
+          " ".join("%d-%d:%d" % (16 * i, 16 * i + 15, n) for i, n in enumerate(h) if n))

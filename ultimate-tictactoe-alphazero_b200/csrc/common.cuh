@@ -145,6 +145,14 @@ cudaError_t launch_heads(const NetWeights& w, const float* act_f32, const __nv_b
 cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
                              int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg = nullptr);
 cudaError_t trunk_tc2_init();
+// only the 5-positions-per-pair instantiation (batches up to trunk_tc2_small_capacity); larger ones go to launch_trunk_pp
+cudaError_t launch_trunk_tc2_small(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
+                                   int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg);
+int trunk_tc2_small_capacity(int n_sm);
+// two groups of positions per CTA pair in flight (net_pp.cu): batches of more than min_count positions
+cudaError_t launch_trunk_pp(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count, int max_rows,
+                            float* skip, int n_sm, cudaStream_t s, long long* dbg, int min_count);
+cudaError_t trunk_pp_init();
 int trunk_tc2_capacity(int n_sm);    // largest batch the cluster variant evaluates in one wave
 int trunk_tc_smem_bytes();
 cudaError_t trunk_tc_init();

@@ -75,9 +75,10 @@ struct uttt_engine {
     float* headfeat;        // [rows][243] head 1x1-conv outputs written by the tensor-core trunk
     float* tc_resid;        // [n_sm][32][512][4] fp32 residual stream of the tensor-core trunk (per CTA)
     int32_t* fwd_count;     // device int for uttt_net_forward
-    long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0 (diagnostics)
+    long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0, then [64] histogram of batch sizes (diagnostics)
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
-    int trunk_variant;      // 1: one CTA per group (net_tc.cu), 2: CTA pair per group (net_tc2.cu)
+    int trunk_variant;      // 1: one CTA per group (net_tc.cu), 2 (default): CTA pair per group (net_tc2.cu) and net_tc.cu above
+                            // 518 positions, 3: net_tc2.cu up to 370 positions, two groups in flight per pair (net_pp.cu) above
     NetWeights w;
     float* raw_res;         // staging for the raw residual conv weights / bn of an upload
     float* raw_res_bn;
@@ -144,7 +145,14 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         // (one wave of CTA pairs) are latency-bound -> cluster variant, larger ones are throughput-bound -> one CTA
         // per group with 4 accumulator tiles.  Counted as ONE trunk launch per round.
         if (ev3) cudaEventRecord(ev3[0], s);
-        if (e->trunk_variant == 2) {
+        if (e->trunk_variant == 3) {
+            // up to one wave of 5-position groups: cluster kernel whose next layer overlaps the epilogue; above: the
+            // two-groups-in-flight kernel (net_pp.cu)
+            const int cap = trunk_tc2_small_capacity(e->n_sm);
+            UTTT_CUDA_OK(launch_trunk_tc2_small(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+            if (max_rows > cap)
+                UTTT_CUDA_OK(launch_trunk_pp(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg, cap));
+        } else if (e->trunk_variant == 2) {
             if (max_rows > trunk_tc2_capacity(e->n_sm))
                 UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
                                              trunk_tc2_capacity(e->n_sm)));
@@ -213,7 +221,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
         ealloc(e, &e->headfeat, R * 243) || ealloc(e, &e->act_a, R * 81 * 128) || ealloc(e, &e->act_b, R * 81 * 128) ||
-        ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128)) {
+        ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128 + 64 + 8)) {
         uttt_destroy(e);
         return 1;
     }
@@ -379,6 +387,7 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
     UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
     UTTT_CUDA_OK(trunk_tc_init());
     UTTT_CUDA_OK(trunk_tc2_init());
+    UTTT_CUDA_OK(trunk_pp_init());
     W.loaded = true;
     return 0;
 }
@@ -683,6 +692,21 @@ int uttt_debug_trunk_timeline(uttt_engine* e, int64_t* out128) {
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     UTTT_CUDA_OK(cudaDeviceSynchronize());
     UTTT_CUDA_OK(cudaMemcpy(out128, e->tc_dbg, 128 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (getenv("UTTT_DEBUG_PHASES")) {      // experiments: kernel entry / setup done / last epilogue done / exit of CTA 0 (cluster trunk)
+        long long ph[4];
+        UTTT_CUDA_OK(cudaMemcpy(ph, e->tc_dbg + 192, sizeof(ph), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "trunk phases (cycles rel. entry): setup %lld, first MMA %lld, last epilogue %lld, exit %lld\n", ph[1] - ph[0],
+                (long long)out128[0] - ph[0], ph[2] - ph[0], ph[3] - ph[0]);
+    }
+    return 0;
+}
+
+int uttt_debug_batch_histogram(uttt_engine* e, int64_t* out64, int32_t reset) {
+    UTTT_CHECK(e && out64, "null argument");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    UTTT_CUDA_OK(cudaDeviceSynchronize());
+    UTTT_CUDA_OK(cudaMemcpy(out64, e->tc_dbg + 128, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (reset) UTTT_CUDA_OK(cudaMemset(e->tc_dbg + 128, 0, 64 * sizeof(long long)));
     return 0;
 }
 

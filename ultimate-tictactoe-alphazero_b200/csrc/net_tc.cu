@@ -70,6 +70,8 @@ trunk_tc_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2][
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_pos = *count;
     if (n_pos <= min_count) return;
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0)          // diagnostics: histogram of evaluator batch sizes (16 per bucket)
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 128 + min(n_pos >> 4, 63), 1ull);
     // positions per group: as few as keeps every group in the first wave (latency matters when the batch is
     // small), at most 5; 4 positions would need the same 4 tiles as 5, so it is never chosen.
     int P = (n_pos + (int)gridDim.x - 1) / (int)gridDim.x;

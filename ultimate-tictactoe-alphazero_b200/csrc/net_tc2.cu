@@ -19,20 +19,10 @@
 //
 // Warp roles (19 warps): 0-15 epilogue (2 tiles x 4 TMEM lane quarters x 2 column halves -- the epilogue is
 // instruction-latency bound, so it wants warps, not wider threads), 16 weight producer, 17-18 MMA issuers.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
-//#define UTTT_TC2_DETAIL 1
-#ifdef UTTT_TC2_DETAIL
-#define DBG_ROW(l) ((l) & 15)          // the detail stamps use rows 16..31
-#else
-#define DBG_ROW(l) (l)
-#endif
-#ifndef UTTT_TC2_NQ
-#define UTTT_TC2_NQ 4
-#endif
-#ifndef UTTT_TC2_NBUF
-#define UTTT_TC2_NBUF 2
-#endif
 
 namespace uttt {
 namespace tc2 {
@@ -59,9 +49,11 @@ struct Cfg {
     static constexpr int STAGES = (LT == 2) ? 8 : 6;
     // LT = 2 has TMEM for two accumulators per tile (4 x 128 = 512 columns): the layers alternate between them, and the
     // epilogue publishes its output per 16-column chunk (NQ act_ready barriers per tile), so the MMAs of layer L+1
-    // run while the epilogue of layer L is still converting the other chunks.
-    static constexpr int NQ = (LT == 2) ? UTTT_TC2_NQ : 1;
-    static constexpr int NBUF = (LT == 2) ? UTTT_TC2_NBUF : 1;
+    // run while the epilogue of layer L is still converting the other chunks.  (LT = 3 has one spare accumulator only;
+    // giving it to tile 0 was measured and does not help: tiles 1 and 2 still wait for their whole epilogue.)
+    static constexpr int NQ = (LT == 2) ? 4 : 1;
+    static constexpr uint32_t ALT_COLS = 256u;                         // column offset of a tile's second accumulator
+    static __host__ __device__ constexpr bool two_accumulators(int) { return LT == 2; }
     static constexpr int BAR_OFF = A_BYTES + STAGES * STAGE_BYTES;
     static constexpr int HEAD_OFF = BAR_OFF + 256;                 // [128*LT rows][4] floats: head partial sums
     static constexpr int SMEM_BYTES = HEAD_OFF + 128 * LT * 16;
@@ -88,13 +80,16 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
     using C = Cfg<LT>;
     constexpr int LOC_TILES = C::LOC_TILES, MAX_P = C::MAX_P, PANEL_BYTES = C::PANEL_BYTES, A_BYTES = C::A_BYTES,
                   STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS,
-                  SKIP_ROWS = C::SKIP_ROWS, NQ = C::NQ, NBUF = C::NBUF;
+                  SKIP_ROWS = C::SKIP_ROWS, NQ = C::NQ;
     extern __shared__ __align__(1024) uint8_t smem[];
+    const long long t_entry = clock64();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
     const int n_pos = *count;
     if (n_pos <= min_count || n_pos > max_count) return;
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0)          // diagnostics: histogram of evaluator batch sizes (16 per bucket)
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 128 + min(n_pos >> 4, 63), 1ull);
     int P = (n_pos + n_pairs - 1) / n_pairs;
     P = P < 1 ? 1 : (P > MAX_P ? MAX_P : P);
     if (P == 4) P = 5;                                // 4 positions need the same 4 tiles as 5
@@ -150,6 +145,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
     const uint32_t peer = rank ^ 1u;
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) { dbg[192] = t_entry; dbg[193] = clock64(); }
 
     int iter = 0;
     for (int g = pair; g < n_groups; g += n_pairs, iter++) {
@@ -223,7 +219,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
             auto epilogue_layer = [&](auto last_tag) {
                 constexpr bool last = decltype(last_tag)::value;
                 const uint32_t lpar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
-                const uint32_t tsrc = taddr + ((NBUF == 2) ? lpar * (uint32_t)(LOC_TILES * 128) : 0u);   // this layer's accumulator
+                const uint32_t tsrc = taddr + (C::two_accumulators(lt) ? lpar * C::ALT_COLS : 0u);       // this layer's accumulator
                 const bool second = (layer >= 0) && (layer & 1) != 0;   // conv2 of a block: add the skip connection
                 const bool keep = second || (layer < 0);                // output is the input of the next block: keep it as skip
                 // the skip connection (8 x 16 B per thread) is fetched from L2 while the MMAs still run
@@ -237,11 +233,8 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
                 if (nb_lo) mbar_wait_spin<false>(bar_accum + 8 * (lt - 1), lpar);
                 if (nb_hi) mbar_wait_spin<false>(bar_accum + 8 * (lt + 1), lpar);
                 if (bnd) mbar_wait_spin<false>(bar_bnd, lpar);    // the peer's boundary-tile MMAs have retired
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[DBG_ROW(layer) * 4 + 2] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
                 tc_fence_after();
-#ifdef UTTT_TC2_DETAIL
-                if (dbg && blockIdx.x == 0 && iter == 0 && lane == 0 && layer == 4) dbg[96 + warp] = clock64();
-#endif
                 float va[16], vb[16];
                 float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
                 tmem_ld16(tsrc, va);
@@ -290,10 +283,6 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
                                     }
                                 }
                             }
-#ifdef UTTT_TC2_DETAIL
-                            if (dbg && blockIdx.x == 0 && iter == 0 && lane == 0 && layer == 4 && ch == 0) dbg[64 + warp] = clock64();
-                            if (dbg && blockIdx.x == 0 && iter == 0 && lane == 0 && layer == 4 && ch == 3) dbg[80 + warp] = clock64();
-#endif
                         }
                     }
                 }
@@ -308,7 +297,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
                         hrow[162] = fmaxf(h2 + o.z + __ldg(headw + 386), 0.0f);
                     }
                 }
-                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[DBG_ROW(layer) * 4 + 3] = clock64();
+                if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 3] = clock64();
             };
 #pragma unroll 1
             for (layer = -1; layer < NET_LAYERS - 1; layer++) epilogue_layer(std::false_type{});
@@ -375,13 +364,13 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
 #pragma unroll 1
             for (int layer = -1; layer < NET_LAYERS; layer++) {
                 const uint32_t apar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
-                const uint32_t tmem_d = tmem_base + (uint32_t)(lt * 128) + ((NBUF == 2) ? apar * (uint32_t)(LOC_TILES * 128) : 0u);
+                const uint32_t tmem_d = tmem_base + (uint32_t)(lt * 128) + (C::two_accumulators(lt) ? apar * C::ALT_COLS : 0u);
                 // accumulator := BN shift (constant panel x bias block); starts the layer's accumulation.  With two
                 // accumulators per tile this needs no activation: it is issued while the previous epilogue still runs.
-                if (NQ == 1 || layer < 0) {
+                if (!C::two_accumulators(lt) || layer < 0) {
 #pragma unroll
                     for (int q = 0; q < NQ; q++) wait_act(q, apar);
-                    if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0) dbg[DBG_ROW(layer) * 4 + 0] = clock64();
+                    if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0) dbg[layer * 4 + 0] = clock64();
                 }
                 next_stage();
                 if (leader) {
@@ -419,15 +408,9 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
 #pragma unroll
                         for (int ks = 0; ks < 4; ks++) {
                             const int m = 4 * s + ks, q = m / 18, r = m % 18, tap = r >> 1, unit = q + 4 * (r & 1);
-                            if (NQ == 4 && r == 0) {
-#ifdef UTTT_TC2_DETAIL
-                                if (dbg && blockIdx.x == 0 && iter == 0 && leader && layer == 5) dbg[112 + lt * 8 + 2 * q] = clock64();
-#endif
+                            if (r == 0 && C::two_accumulators(lt)) {
                                 wait_act(q, apar);
-#ifdef UTTT_TC2_DETAIL
-                                if (dbg && blockIdx.x == 0 && iter == 0 && leader && layer == 5) dbg[113 + lt * 8 + 2 * q] = clock64();
-#endif
-                                if (q == 0 && dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[DBG_ROW(layer) * 4 + 0] = clock64();
+                                if (q == 0 && dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[layer * 4 + 0] = clock64();
                             }
                             const int off = (tap / 3 - 1) * 10 + (tap % 3 - 1) + 2 * unit * (PANEL_BYTES / 16);
                             if (leader) umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)off, b_st + (uint64_t)(ks * 256), IDESC, 1u);
@@ -437,7 +420,7 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
                             if (s == STAGES_PER_LAYER - 1) {
                                 umma_commit(bar_accum + 8 * lt);
                                 if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
-                                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0) dbg[DBG_ROW(layer) * 4 + 1] = clock64();
+                                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0) dbg[layer * 4 + 1] = clock64();
                             }
                         }
                         advance();
@@ -448,12 +431,14 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2]
         }
     }
 
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[194] = clock64();
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                 // nobody exits while the peer may still write its margins / barriers
     if (warp == EPI_WARPS + 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[195] = clock64();
 }
 
 }  // namespace tc2
@@ -468,6 +453,18 @@ cudaError_t trunk_tc2_init() {
 
 // largest batch the CTA-pair variants evaluate in one wave (7 positions per pair)
 int trunk_tc2_capacity(int n_sm) { return (n_sm / 2) * tc2::Cfg<3>::MAX_P; }
+
+int trunk_tc2_small_capacity(int n_sm) { return (n_sm / 2) * tc2::Cfg<2>::MAX_P; }
+
+cudaError_t launch_trunk_tc2_small(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
+                                   int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg) {
+    int pairs = n_sm / 2;
+    if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
+    tc2::trunk_tc2_kernel<2><<<2 * pairs, tc2::Cfg<2>::THREADS, tc2::Cfg<2>::SMEM_BYTES, s>>>(
+        w.res_w_bf16, w.conv_in_w_bf16, w.bias_blk, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, 0,
+        trunk_tc2_small_capacity(n_sm), dbg);
+    return cudaGetLastError();
+}
 
 // Two instantiations are enqueued; the queue length read on the device selects one:
 //   batch <= 5 * pairs : 2 accumulator tiles per CTA (lowest latency, 8-stage weight ring)

@@ -71,6 +71,7 @@ ABI = {
                                   C.c_int32, _vp, _vp], C.c_int),
     "uttt_selfplay_fetch": ([_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp], C.c_int),
     "uttt_debug_trunk_timeline": ([_vp, _vp], C.c_int),
+    "uttt_debug_batch_histogram": ([_vp, _vp, C.c_int32], C.c_int),
     "uttt_last_run_profile": ([_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
 }
 
@@ -363,6 +364,12 @@ class Engine:
         out = np.zeros(128, np.int64)
         _check(self.lib.uttt_debug_trunk_timeline(self.h, _ptr(out)))
         return out.reshape(32, 4)
+
+    def batch_histogram(self, reset=True):
+        """launch counts of the tensor-core trunk by evaluator batch size, 64 buckets of 16 positions"""
+        out = np.zeros(64, np.int64)
+        _check(self.lib.uttt_debug_batch_histogram(self.h, _ptr(out), 1 if reset else 0))
+        return out
 
     def last_run_profile(self):
         """-> {kind: (ms, launches)} for tree / trunk / heads / all kernels of the last self-play run"""
