@@ -69,7 +69,12 @@ def full(name):
         f.write("# ncu --set full, %s kernel, round %s\n\n" % (name, tag))
         f.write("`ncu --set full --clock-control none --import-source on -k regex:<kernel> ...` on tools/trunk_timeline.py "
                 "(trunk: steady batch) / tools/prof_selfplay.py --games 500 (tree)\n\n")
+        seen = set()
         for r in rows[2:]:
+            kname = r[hdr.index("Kernel Name")].split("(")[0]
+            if name == "rules" and kname in seen:      # several timed repetitions per kernel: keep the first
+                continue
+            seen.add(kname)
             f.write("## launch id %s: %s grid %s block %s\n\n| metric | unit | value |\n|---|---|---:|\n" % (
                 r[0], r[hdr.index("Kernel Name")].split("(")[0], r[hdr.index("Grid Size")], r[hdr.index("Block Size")]))
             for i, h in enumerate(hdr):
@@ -84,3 +89,4 @@ full("trunk1")     # trunk_tc_kernel     (one CTA per group; batch of 740 positi
 full("trunk2")     # trunk_tc2_kernel<2> (CTA pair per group, 2 tiles per CTA; batch of 345 positions)
 full("trunk3")     # trunk_tc2_kernel<3> (CTA pair per group, 3 tiles per CTA; batch of 500 positions)
 full("tree")
+full("rules")      # step / legal / encode / gather_planes / playout kernels at 2^22 (2^20) states (tools/prof_rules.py 22)
