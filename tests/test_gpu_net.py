@@ -248,49 +248,55 @@ def test_fp32_trunk_vs_reference_golden_outputs(setup, golden_dir):
 
 
 def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
-    """The trunk kernel is chosen on the device from the batch size (CTA pairs with 2 or 3 tiles per CTA, one CTA per
-    group above 518 positions) and the group size from ceil(n / pairs): every boundary of that dispatch must produce
-    the same rows.  The CTA-pair kernels accumulate every row in the same order: bit-identical."""
+    """The trunk kernel is chosen on the device from the batch size and the group sizes from ceil(n / pairs): every
+    boundary of that dispatch must produce the same rows.  Default (UTTT_TRUNK=3): one group per CTA pair up to 370
+    positions (net_tc2.cu), two groups in flight above (net_pp.cu, cta_group::2).  All of them accumulate a row in the
+    same order -- bit-identical -- except the one-tile group of the 6/7-positions-per-pair case (371..518 positions),
+    whose K loop is split over two accumulators: fp32 re-association, checked on a well-conditioned network."""
+    import copy
     import engine
     e, model, sts = setup
     big = np.concatenate([sts] * 5)[:1600]
-    e2 = engine.Engine(n_slots=800, max_sims=50, max_batch=8, max_games=8)
-    try:
-        e2.upload_model(model)
-        ref_p, ref_v = _forward(e2, big[:800], engine.EVAL_NET_BF16)      # one CTA per group (n > 518)
-        pair_p, pair_v = _forward(e2, big[:518], engine.EVAL_NET_BF16)    # CTA pairs, 3 tiles per CTA
-        # the two families sum the heads' 1x1 convs in a different order (whole row vs two column halves); on the
-        # ill-conditioned random-init net (logits up to +-400) that fp32 reordering shows up at the 1e-5 level
-        assert np.abs(pair_p - ref_p[:518]).max() < 1e-3 and np.abs(pair_v - ref_v[:518]).max() < 1e-3
-        f32_p, _ = _forward(e2, big[:64], engine.EVAL_NET_FP32)
-        assert (ref_p[:64].argmax(1) == f32_p.argmax(1)).mean() > 0.9
-        for n in (1, 2, 3, 73, 74, 75, 147, 148, 149, 221, 222, 223, 295, 296, 297, 369, 370, 371, 372, 443, 444, 445,
-                  500, 517, 518, 519, 520, 739, 740, 741, 800):
-            p, v = _forward(e2, big[:n], engine.EVAL_NET_BF16)
-            rp, rv = (pair_p, pair_v) if n <= 518 else (ref_p, ref_v)
-            assert (p == rp[:n]).all() and (v == rv[:n]).all(), n
-    finally:
-        e2.close()
-    # UTTT_TRUNK=3: two groups of positions in flight per CTA pair above 370 positions (net_pp.cu, experimental: same
-    # rows bit for bit, also when a pair loops over several super-groups); UTTT_TRUNK=1: one CTA per group only
-    monkeypatch.setenv("UTTT_TRUNK", "3")
+    damped = _damped(copy.deepcopy(model))
     e3 = engine.Engine(n_slots=1600, max_sims=50, max_batch=8, max_games=8)
     try:
+        for net, tol in ((model, None), (damped, TOL)):     # TOL = 1e-2, the bar of the bf16 path against fp32
+            e3.upload_model(net)
+            ref_p, ref_v = _forward(e3, big[:370], engine.EVAL_NET_BF16)     # one group per pair
+            big_p, big_v = _forward(e3, big, engine.EVAL_NET_BF16)           # 3 super-groups of 2 x 5 positions on some pairs
+            assert (big_p[:370] == ref_p).all() and (big_v[:370] == ref_v).all()
+            for n in (1, 2, 3, 73, 74, 75, 147, 148, 149, 221, 222, 223, 295, 296, 297, 369, 370, 371, 372, 443, 444, 445,
+                      500, 517, 518, 519, 520, 591, 592, 593, 665, 666, 667, 739, 740, 741, 800, 1111, 1480, 1481):
+                p, v = _forward(e3, big[:n], engine.EVAL_NET_BF16)
+                if 370 < n <= 518:
+                    ptot = -(-n // 74)
+                    split = (np.arange(n) % ptot) >= 5                        # positions of the one-tile group
+                    assert (p[~split] == big_p[:n][~split]).all() and (v[~split] == big_v[:n][~split]).all(), n
+                    if tol is None:      # random init: logits up to +-400, any rounding difference can flip a near tie
+                        assert (p[split].argmax(1) == big_p[:n][split].argmax(1)).mean() > 0.9, n
+                    else:
+                        assert np.abs(p - big_p[:n]).max() < tol and np.abs(v - big_v[:n]).max() < tol, n
+                else:
+                    assert (p == big_p[:n]).all() and (v == big_v[:n]).all(), n
         e3.upload_model(model)
-        for n in (370, 371, 444, 445, 500, 518, 519, 592, 593, 666, 667, 740, 741, 1111, 1480, 1481, 1600):
-            p, v = _forward(e3, big[:n], engine.EVAL_NET_BF16)
-            m = min(n, 518)
-            assert (p[:m] == pair_p[:m]).all() and (v[:m] == pair_v[:m]).all(), n
-            m = min(n, 800)
-            assert np.abs(p[:m] - ref_p[:m]).max() < 1e-3, n
+        ref_p, ref_v = _forward(e3, big[:800], engine.EVAL_NET_BF16)
+        f32_p, _ = _forward(e3, big[:64], engine.EVAL_NET_FP32)
+        assert (ref_p[:64].argmax(1) == f32_p.argmax(1)).mean() > 0.9
     finally:
         e3.close()
-    monkeypatch.setenv("UTTT_TRUNK", "1")
-    e1 = engine.Engine(n_slots=800, max_sims=50, max_batch=8, max_games=8)
-    try:
-        e1.upload_model(model)
-        for n in (3, 300, 800):
-            p, v = _forward(e1, big[:n], engine.EVAL_NET_BF16)
-            assert (p == ref_p[:n]).all() and (v == ref_v[:n]).all(), n
-    finally:
-        e1.close()
+    # the earlier kernel families stay selectable: UTTT_TRUNK=2 (CTA pairs with 2 or 3 tiles per CTA up to 518 positions,
+    # one CTA per group above), UTTT_TRUNK=1 (one CTA per group only).  The one-CTA kernel sums the heads' 1x1 convs in
+    # another order (whole row vs two column halves): ~1e-5 on the ill-conditioned random-init net
+    for variant in ("2", "1"):
+        monkeypatch.setenv("UTTT_TRUNK", variant)
+        ev = engine.Engine(n_slots=800, max_sims=50, max_batch=8, max_games=8)
+        try:
+            ev.upload_model(model)
+            for n in (3, 300, 370, 500, 518, 800):
+                p, v = _forward(ev, big[:n], engine.EVAL_NET_BF16)
+                if variant == "2" and n <= 518:
+                    assert (p == ref_p[:n]).all() and (v == ref_v[:n]).all(), (variant, n)
+                else:
+                    assert np.abs(p - ref_p[:n]).max() < 1e-3 and np.abs(v - ref_v[:n]).max() < 1e-3, (variant, n)
+        finally:
+            ev.close()

@@ -119,6 +119,11 @@ struct NetWeights {
     __nv_bfloat16* conv_in_w_bf16;   // conv_input as a K=16-per-tap tensor-core layer: [12 taps (9 used)][2][128][8]
     float* bias_all;                 // [33][128]: conv_input shift followed by the 32 trunk layers' shifts
     __nv_bfloat16* bias_blk;         // [33][2][128][8] bf16: each layer's shift as a tensor-core B block (hi, lo in k = 0, 1)
+    // the same three arrays for cta_group::2 MMAs (net_pp.cu): the B operand is split by output channel between the two
+    // CTAs of a pair, and a CTA's share of a weight stage is contiguous: [stage][cta rank 2][blocks][2 k-panels][64 co][8]
+    __nv_bfloat16* res_w_2sm;        // [32*9 stages][2][8 blocks]...
+    __nv_bfloat16* conv_in_w_2sm;    // [2 stages][2][8 taps]... (16 tap slots, 9 used)
+    __nv_bfloat16* bias_blk_2sm;     // [33][2][1 block]...
     float* head_w;                   // [3][128] policy conv (2 rows) + value conv, BN scale folded; [384..386] BN shifts
     // heads (fp32): policy conv [2][128] + shift[2], fc [81][162] + b; value conv [128] + shift, fc1 [256][81]+b, fc2 [256]+b
     float* pol_conv_w; float* pol_conv_b; float* pol_fc_w; float* pol_fc_b;
@@ -150,6 +155,7 @@ cudaError_t launch_trunk_tc2_small(const NetWeights& w, const __nv_bfloat16* pla
                                    int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg);
 int trunk_tc2_small_capacity(int n_sm);
 // two groups of positions per CTA pair in flight (net_pp.cu): batches of more than min_count positions
+cudaError_t launch_split_weights_2sm(const __nv_bfloat16* src, __nv_bfloat16* dst, int n_blocks, int blocks_per_stage, cudaStream_t s);
 cudaError_t launch_trunk_pp(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count, int max_rows,
                             float* skip, int n_sm, cudaStream_t s, long long* dbg, int min_count);
 cudaError_t trunk_pp_init();

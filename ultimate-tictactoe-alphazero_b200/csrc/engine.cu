@@ -77,8 +77,9 @@ struct uttt_engine {
     int32_t* fwd_count;     // device int for uttt_net_forward
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0, then [64] histogram of batch sizes (diagnostics)
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
-    int trunk_variant;      // 1: one CTA per group (net_tc.cu), 2 (default): CTA pair per group (net_tc2.cu) and net_tc.cu above
-                            // 518 positions, 3: net_tc2.cu up to 370 positions, two groups in flight per pair (net_pp.cu) above
+    int trunk_variant;      // 3 (default): CTA pair per group (net_tc2.cu) up to 370 positions, two groups in flight per pair with
+                            // cta_group::2 MMAs (net_pp.cu) above; for comparison 2: net_tc2.cu (2 or 3 tiles per CTA) up to 518
+                            // positions and net_tc.cu above, 1: one CTA per group (net_tc.cu) only
     NetWeights w;
     float* raw_res;         // staging for the raw residual conv weights / bn of an upload
     float* raw_res_bn;
@@ -198,7 +199,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     memset(&e->tp, 0, sizeof(e->tp));
     memset(&e->w, 0, sizeof(e->w));
     e->cfg = *cfg;
-    e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 2;
+    e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 3;
     e->lane_threshold = getenv("UTTT_LANE_THRESHOLD") ? atoi(getenv("UTTT_LANE_THRESHOLD")) : 1024;
     cudaDeviceProp prop;
     UTTT_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -221,7 +222,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
         ealloc(e, &e->headfeat, R * 243) || ealloc(e, &e->act_a, R * 81 * 128) || ealloc(e, &e->act_b, R * 81 * 128) ||
-        ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128 + 64 + 8)) {
+        ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128 + 64 + 8 + 16)) {
         uttt_destroy(e);
         return 1;
     }
@@ -248,7 +249,7 @@ int uttt_destroy(uttt_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
-    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, e->w.head_w, e->w.pol_conv_w,
+    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, e->w.head_w, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b};
     for (float* p : wp) if (p) cudaFree(p);
@@ -371,6 +372,17 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
             }
         if (!W.bias_blk) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_blk, bb.size() * sizeof(__nv_bfloat16)));
         UTTT_CUDA_OK(cudaMemcpy(W.bias_blk, bb.data(), bb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        // per-CTA halves of the three B-operand arrays for the cta_group::2 trunk
+        const size_t blk = 2 * 128 * 8;
+        if (!W.res_w_2sm) UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_2sm, (size_t)32 * 72 * blk * sizeof(__nv_bfloat16)));
+        if (!W.conv_in_w_2sm) {
+            UTTT_CUDA_OK(cudaMalloc((void**)&W.conv_in_w_2sm, (size_t)16 * blk * sizeof(__nv_bfloat16)));
+            UTTT_CUDA_OK(cudaMemset(W.conv_in_w_2sm, 0, (size_t)16 * blk * sizeof(__nv_bfloat16)));
+        }
+        if (!W.bias_blk_2sm) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_blk_2sm, (size_t)33 * blk * sizeof(__nv_bfloat16)));
+        UTTT_CUDA_OK(launch_split_weights_2sm(W.res_w_bf16, W.res_w_2sm, 32 * 72, 8, e->stream));
+        UTTT_CUDA_OK(launch_split_weights_2sm(W.conv_in_w_bf16, W.conv_in_w_2sm, 12, 8, e->stream));
+        UTTT_CUDA_OK(launch_split_weights_2sm(W.bias_blk, W.bias_blk_2sm, 33, 1, e->stream));
     }
     {
         std::vector<float> hw(387);
@@ -695,6 +707,11 @@ int uttt_debug_trunk_timeline(uttt_engine* e, int64_t* out128) {
     if (getenv("UTTT_DEBUG_PHASES")) {      // experiments: kernel entry / setup done / last epilogue done / exit of CTA 0 (cluster trunk)
         long long ph[4];
         UTTT_CUDA_OK(cudaMemcpy(ph, e->tc_dbg + 192, sizeof(ph), cudaMemcpyDeviceToHost));
+        long long d[16];
+        UTTT_CUDA_OK(cudaMemcpy(d, e->tc_dbg + 160, sizeof(d), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "pp detail layer 20 (rel): A: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld | B: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld\n",
+                0ll, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - d[0], d[8] - d[0], d[9] - d[0], d[10] - d[0], d[11] - d[0],
+                d[12] - d[0], d[13] - d[0], d[14] - d[0]);
         fprintf(stderr, "trunk phases (cycles rel. entry): setup %lld, first MMA %lld, last epilogue %lld, exit %lld\n", ph[1] - ph[0],
                 (long long)out128[0] - ph[0], ph[2] - ph[0], ph[3] - ph[0]);
     }

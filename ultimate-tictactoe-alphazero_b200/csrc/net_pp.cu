@@ -32,16 +32,18 @@ constexpr int POS_ROWS = 100;
 constexpr int LEAD = 11;
 constexpr int LT = 2;                           // accumulator tiles per CTA of group A (and the number of issuer warps)
 constexpr int NG = 2;                           // groups in flight
-constexpr int STAGE_BYTES = 16384;
-constexpr int STAGES_PER_LAYER = 18;
-constexpr int IN_STAGES = 3;
-constexpr int BIAS_BYTES = 4096;
+constexpr int STAGE_BLOCKS = 8;                 // K-blocks (MMAs per tile pair) per weight stage: the issuer threads pay one
+                                                // barrier wait and one commit (200+ cycles each) per stage
+constexpr int STAGE_BYTES = STAGE_BLOCKS * 2048; // per CTA: its output-channel half of the stage's K-blocks
+constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
+constexpr int IN_STAGES = 2;                    // conv_input: 16 tap slots (9 used)
+constexpr int BIAS_BYTES = 2048;                // per CTA
 constexpr int CONST_BYTES = 4096;
 constexpr int EPI_WARPS = 8 * LT;
 constexpr int THREADS = (EPI_WARPS + 1 + LT) * 32;
 constexpr int SKIP_ROWS = 128 * LT;
 constexpr int GROUP_LAYERS = NET_LAYERS + 1;    // conv_input runs as layer -1 through the same pipeline
-constexpr uint32_t IDESC = IDESC_M128_N128_BF16;
+constexpr uint32_t IDESC = IDESC_M256_N128_BF16; // cta_group::2: 128 rows of each CTA x all 128 output channels
 constexpr int a_rows(int tiles) { return (LEAD + 128 * tiles + 11 + 7) / 8 * 8; }
 
 // LTB = accumulator tiles per CTA of group B: 1 (B holds up to 2 positions: 7 per pair, a deeper weight ring) or
@@ -55,7 +57,7 @@ struct Cfg {
     static constexpr int W_OFF = CONST_OFF + CONST_BYTES;
     static constexpr int STAGES = (LTB == 1) ? 6 : 4;
     static constexpr int BAR_OFF = W_OFF + STAGES * STAGE_BYTES;
-    static constexpr int HEAD_OFF = BAR_OFF + 256;        // [128*LT rows][4] floats: head partial sums
+    static constexpr int HEAD_OFF = BAR_OFF + 512;        // [128*LT rows][4] floats: head partial sums
     static constexpr int SMEM_BYTES = HEAD_OFF + 128 * LT * 16;
     static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
@@ -63,7 +65,8 @@ struct Cfg {
 // geometry of one group inside its CTA pair (uniform per CTA)
 struct Geo {
     int P;          // positions
-    int T0;         // tiles of rank 0
+    int T0;         // tiles of rank 0 (= MMA pair indices in use: rank 0 never has fewer tiles than rank 1)
+    int T1;         // tiles of rank 1
     int tiles;      // tiles of this CTA
     int tile0;      // first tile of this CTA within the group
     int bnd_tile;   // local tile that touches the peer's rows
@@ -74,6 +77,7 @@ __device__ __forceinline__ Geo make_geo(int P, uint32_t rank) {
     g.P = P;
     const int T = (P * POS_ROWS + 127) / 128;
     g.T0 = (T + 1) >> 1;
+    g.T1 = T - g.T0;
     g.tiles = (rank == 0) ? g.T0 : T - g.T0;
     g.tile0 = (rank == 0) ? 0 : g.T0;
     g.has_peer = (T - g.T0) > 0;
@@ -83,9 +87,9 @@ __device__ __forceinline__ Geo make_geo(int P, uint32_t rank) {
 
 template <int LTB>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
-trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks][2][128][8] bf16
-                const __nv_bfloat16* __restrict__ wq_in,     // conv_input: [12 taps (9 used)][2][128][8] bf16
-                const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
+trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32*9 stages][2 ranks][8 K-blocks][2][64][8] bf16
+                const __nv_bfloat16* __restrict__ wq_in,     // conv_input: [2 stages][2 ranks][8 taps][2][64][8] bf16
+                const __nv_bfloat16* __restrict__ wq_bias,   // [33][2 ranks][2][64][8] bf16: per layer the BN shift as a K=16 B block
                 const __nv_bfloat16* __restrict__ planes,    // network input [rows][3][81] bf16
                 const float* __restrict__ headw,             // [3][128] policy conv (2) + value conv; [384..386] shifts
                 float* headfeat,                             // out: [rows][243]
@@ -111,7 +115,7 @@ trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks
     if (pair >= n_super) return;                              // both CTAs of the pair take the same branch
     const int PA = Ptot < MAX_P ? Ptot : MAX_P;
     const Geo geo[NG] = {make_geo(PA, rank), make_geo(Ptot - PA, rank)};
-    const bool any_tiles = geo[0].tiles + geo[1].tiles > 0;
+    const bool any_tiles = geo[0].T0 + geo[1].T0 > 0;         // pair-level: both CTAs stream the weights of a group that exists
 
     uint8_t* sA = smem;
     const uint32_t sA_u = smem_u32(sA);
@@ -120,33 +124,41 @@ trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks
     auto grp_off = [](int g) { return (uint32_t)(g == 0 ? 0 : C::A_BYTES); };
     auto grp_panel = [](int g) { return (uint32_t)(g == 0 ? C::PANEL_A : C::PANEL_B); };
     const uint32_t bar_u = sA_u + BAR_OFF;
-    // barriers: full[STAGES], empty[STAGES], then per group accum[LT], act[LT], bnd; then the tmem base holder
+    // barriers: full[STAGES], empty[STAGES], then per group accum[LT], act[LT]; then the tmem base holder.  The leader's
+    // full / act barriers also count an arrive forwarded by the peer ("my half of the stage has landed" / "my rows of the
+    // tile pair are in place"), so its issuers wait on one barrier per event.
     const uint32_t bar_full = bar_u, bar_empty = bar_u + 8 * STAGES, bar_grp = bar_u + 16 * STAGES;
-    constexpr int GRP_BARS = 2 * LT + 1;
+    constexpr int GRP_BARS = 2 * LT;
     auto bar_accum = [&](int g, int t) { return bar_grp + 8u * (uint32_t)(g * GRP_BARS + t); };
     auto bar_act = [&](int g, int t) { return bar_grp + 8u * (uint32_t)(g * GRP_BARS + LT + t); };
-    auto bar_bnd = [&](int g) { return bar_grp + 8u * (uint32_t)(g * GRP_BARS + 2 * LT); };
-    static_assert(16 * STAGES + 8 * NG * GRP_BARS + 4 <= 256, "barrier block");
+    static_assert(16 * STAGES + 8 * NG * GRP_BARS + 4 <= 512, "barrier block");
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * STAGES + 8 * NG * GRP_BARS);
+    // group B of the 7-positions instantiation has one tile pair: its K loop is split between the two issuer threads
+    // (even / odd weight stages) into two accumulators that the epilogue adds, because one thread cannot issue
+    // 64-cycle MMAs fast enough (every shared-memory barrier operation of the issuer takes 200+ cycles while the tensor
+    // pipe saturates shared memory: measured ~107 cycles per MMA and thread)
+    auto split_k = [&](int g) { return LTB == 1 && g == 1; };
     const int bnd_quarter = (rank == 0) ? 3 : 0;              // the quarter-warp that owns the rows next to the peer
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, LT); }
+        for (int i = 0; i < STAGES; i++) {
+            mbar_init(bar_full + 8 * i, rank == 0 ? 2 : 1);      // own producer (+ the peer's forwarded arrive)
+            mbar_init(bar_empty + 8 * i, LT);                     // multicast commits of the leader's LT issuers
+        }
         for (int g = 0; g < NG; g++) {
             for (int t = 0; t < LT; t++) {
-                mbar_init(bar_accum(g, t), 1);
+                mbar_init(bar_accum(g, t), split_k(g) ? 2 : 1);
                 // own 8 epilogue warps + the 2 boundary warps of each row neighbour (the peer's halo rows arrive as
-                // transaction bytes)
-                mbar_init(bar_act(g, t), 8 + (t > 0 ? 2 : 0) + (t < geo[g].tiles - 1 ? 2 : 0));
+                // transaction bytes) + on the leader the peer's forwarded arrive for its tile of the same index
+                mbar_init(bar_act(g, t), 8 + (t > 0 ? 2 : 0) + (t < geo[g].tiles - 1 ? 2 : 0) + ((rank == 0 && t < geo[g].T1) ? 1 : 0));
             }
-            mbar_init(bar_bnd(g), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == EPI_WARPS + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u)
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(512u)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < (C::A_BYTES + C::B_BYTES) / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
     // constant A block: every row = (1, 1, 0, ..., 0).  One extra K=16 MMA per tile and layer multiplies it with the
@@ -251,17 +263,27 @@ trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks
                 mbar_wait_spin<false>(bar_accum(g, lt), lpar);
                 if (r.nb_lo) mbar_wait_spin<false>(bar_accum(g, lt - 1), lpar);
                 if (r.nb_hi) mbar_wait_spin<false>(bar_accum(g, lt + 1), lpar);
-                if (r.bnd) mbar_wait_spin<false>(bar_bnd(g), lpar);      // the peer's boundary-tile MMAs have retired
+                // the peer's boundary tile has retired too: its MMAs are the other half of the pair MMAs of index 0 (rank 1's
+                // first tile) / T0-1 (rank 0's last tile), whose commits arrive on this CTA's barrier of that index
+                if (r.bnd) mbar_wait_spin<false>(bar_accum(g, (rank == 0) ? 0 : geo[g].T0 - 1), lpar);
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0 && layer < 16) dbg[(16 * g + layer) * 4 + 2] = clock64();
                 tc_fence_after();
+                const bool dual = split_k(g) && layer >= 0;         // two partial accumulators (columns +128): add them
                 float va[16], vb[16];
                 float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
                 tmem_ld16(taddr, va);
 #pragma unroll
                 for (int ch = 0; ch < 4; ch++) {
                     float* v = (ch & 1) ? vb : va;
+                    float* o = (ch & 1) ? va : vb;
                     tmem_ld_wait();
-                    if (ch < 3) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
+                    if (dual) {
+                        tmem_ld16(taddr + 128u + (uint32_t)(ch * 16), o);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] += o[j];
+                    }
+                    if (ch < 3) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), o);
                     f16x8_add2(sk[2 * ch], v);
                     f16x8_add2(sk[2 * ch + 1], v + 8);
                     if constexpr (last) {
@@ -316,14 +338,14 @@ trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks
 #pragma unroll 1
             for (int g = 0; g < NG; g++) epilogue_layer(g, NET_LAYERS - 1, std::true_type{});
         } else if (warp == EPI_WARPS) {
-            // ================= weight producer: every layer once per group that has tiles in this CTA =================
+            // ================= weight producer: this CTA's output-channel half of every layer, once per group =========
             if (!any_tiles) continue;
             int stage = 0;
             uint32_t par = 0;
             {
                 // the ring position continues across super-groups
                 int per_group = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);
-                int gn = iter * per_group * ((geo[0].tiles > 0) + (geo[1].tiles > 0));
+                int gn = iter * per_group * ((geo[0].T0 > 0) + (geo[1].T0 > 0));
                 stage = gn % STAGES;
                 par = (uint32_t)((gn / STAGES) & 1);
             }
@@ -332,16 +354,16 @@ trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks
                 const int n_st = 1 + ((layer < 0) ? IN_STAGES : STAGES_PER_LAYER);
 #pragma unroll 1
                 for (int g = 0; g < NG; g++) {
-                    if (geo[g].tiles == 0) continue;
+                    if (geo[g].T0 == 0) continue;
 #pragma unroll 1
                     for (int st = 0; st < n_st; st++) {
                         mbar_wait(bar_empty + 8 * stage, par ^ 1u);
                         if (lane == 0) {
                             const __nv_bfloat16* src;
                             uint32_t bytes = STAGE_BYTES;
-                            if (st == 0) { src = wq_bias + (size_t)(layer + 1) * (BIAS_BYTES / 2); bytes = BIAS_BYTES; }
-                            else if (layer < 0) src = wq_in + (size_t)(st - 1) * (STAGE_BYTES / 2);
-                            else src = wq + (size_t)(layer * STAGES_PER_LAYER + st - 1) * (STAGE_BYTES / 2);
+                            if (st == 0) { src = wq_bias + (size_t)((layer + 1) * 2 + (int)rank) * (BIAS_BYTES / 2); bytes = BIAS_BYTES; }
+                            else if (layer < 0) src = wq_in + (size_t)((st - 1) * 2 + (int)rank) * (STAGE_BYTES / 2);
+                            else src = wq + (size_t)((layer * STAGES_PER_LAYER + st - 1) * 2 + (int)rank) * (STAGE_BYTES / 2);
                             mbar_expect_tx(bar_full + 8 * stage, bytes);
                             bulk_g2s(sB_u + stage * STAGE_BYTES, src, bytes, bar_full + 8 * stage);
                         }
@@ -350,95 +372,155 @@ trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks
                     }
                 }
             }
+        } else if (rank != 0) {
+            // ================= rank 1 has no MMAs to issue (the leader issues for the pair): its two issuer warps forward
+            // its barriers to the leader.  Warp EPI_WARPS+1: "my half of weight stage i has landed"; warp EPI_WARPS+2: "my
+            // rows of tile pair t of group g are in place".  CTA-scope arrives on the leader's barriers (no MEMBAR.GPU): the
+            // data they announce sit in THIS CTA's shared memory, fenced for the async proxy by their writers, and are read
+            // by this CTA's tensor pipe when the leader's MMA executes.
+            if (!any_tiles) continue;
+            if (warp == EPI_WARPS + 1) {
+                int stage = 0;
+                uint32_t par = 0;
+                {
+                    int per_group = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);
+                    int gn = iter * per_group * ((geo[0].T0 > 0) + (geo[1].T0 > 0));
+                    stage = gn % STAGES;
+                    par = (uint32_t)((gn / STAGES) & 1);
+                }
+                const int total = ((geo[0].T0 > 0) + (geo[1].T0 > 0)) * ((IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1));
+#pragma unroll 1
+                for (int i = 0; i < total; i++) {
+                    mbar_wait_spin<false>(bar_full + 8 * stage, par);
+                    if (lane == 0) mbar_arrive_peer(map_to_rank(bar_full + 8 * stage, 0));
+                    __syncwarp();
+                    if (++stage == STAGES) { stage = 0; par ^= 1u; }
+                }
+            } else {
+#pragma unroll 1
+                for (int layer = -1; layer < NET_LAYERS; layer++) {
+                    const uint32_t apar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
+#pragma unroll 1
+                    for (int g = 0; g < NG; g++) {
+#pragma unroll 1
+                        for (int t = 0; t < geo[g].T1; t++) {
+                            mbar_wait_spin<false>(bar_act(g, t), apar);
+                            if (lane == 0) mbar_arrive_peer(map_to_rank(bar_act(g, t), 0));
+                            __syncwarp();
+                        }
+                    }
+                }
+            }
         } else {
-            // ================= MMA issuers: warp EPI_WARPS+1+t drives local accumulator tile t of both groups ==========
+            // ================= leader CTA: warp EPI_WARPS+1+t issues the pair MMAs (cta_group::2, M = 256: tile t of this CTA
+            // and tile t of the peer) of both groups ==========
             if (!any_tiles) continue;
             const int lt = warp - (EPI_WARPS + 1);
             const bool leader = elect_one();
-            const uint64_t b_desc = make_desc(sB_u, 2048, 128);
+            const uint64_t b_desc = make_desc(sB_u, 1024, 128);           // this CTA's 64 output channels: [2 panels][64][8]
             const uint64_t bias_a = make_desc(sA_u + CONST_OFF, 2048, 128);
             int stage = 0;
             uint32_t par = 0;
             {
                 int per_group = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);
-                int gn = iter * per_group * ((geo[0].tiles > 0) + (geo[1].tiles > 0));
+                int gn = iter * per_group * ((geo[0].T0 > 0) + (geo[1].T0 > 0));
                 stage = gn % STAGES;
                 par = (uint32_t)((gn / STAGES) & 1);
             }
             uint64_t b_st = 0;
-            auto next_stage = [&]() {              // waits for the next weight stage; b_st = descriptor of its first block
+            auto next_stage = [&]() {              // both halves of the next weight stage have landed; b_st = its first block
                 mbar_wait_spin<false>(bar_full + 8 * stage, par);
                 tc_fence_after();
                 b_st = b_desc + (uint64_t)(uint32_t)(stage * (STAGE_BYTES / 16));
             };
+            auto release_stage = [&]() {           // frees the stage in both CTAs when the MMAs issued so far retire
+                umma_commit_2sm(bar_empty + 8 * stage, (uint16_t)3);
+            };
             auto advance = [&]() {
                 if (++stage == STAGES) { stage = 0; par ^= 1u; }
             };
+            // per group, fixed for the kernel: does this thread issue for it, into which accumulator, from which rows
+            bool g_stream[NG], g_issue[NG], g_split[NG];
+            uint32_t g_tmem[NG], g_act[NG], g_accum[NG];
+            uint64_t g_adesc[NG];
+            int g_panel16[NG];
+#pragma unroll
+            for (int g = 0; g < NG; g++) {
+                const Geo& G = geo[g];
+                g_split[g] = split_k(g);
+                const int tile = g_split[g] ? 0 : lt;           // split K: both issuers work on tile pair 0
+                g_stream[g] = G.T0 > 0;
+                g_issue[g] = tile < G.T0;
+                g_tmem[g] = tmem_base + (uint32_t)((g * LT + (g_split[g] ? lt : tile)) * 128);
+                g_act[g] = bar_act(g, tile);
+                g_accum[g] = bar_accum(g, tile);
+                g_panel16[g] = (int)(grp_panel(g) / 16);
+                g_adesc[g] = make_desc(sA_u + grp_off(g) + (uint32_t)(LEAD + tile * 128) * 16u, grp_panel(g), 128);
+            }
 #pragma unroll 1
             for (int layer = -1; layer < NET_LAYERS; layer++) {
                 const uint32_t apar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
-#pragma unroll 1
+#pragma unroll
                 for (int g = 0; g < NG; g++) {
-                    const Geo& G = geo[g];
-                    if (G.tiles == 0) continue;                     // nobody in this CTA streams this group's weights
-                    const bool mine = lt < G.tiles;                 // otherwise: walk and release the stages only
-                    const bool issue = mine && leader;
-                    const bool signal_peer = G.has_peer && (lt == G.bnd_tile);
-                    const uint32_t tmem_d = tmem_base + (uint32_t)((g * LT + lt) * 128);
-                    const uint32_t PANEL_BYTES = grp_panel(g);
-                    const int panel16 = (int)(PANEL_BYTES / 16);
-                    const uint64_t a_desc = make_desc(sA_u + grp_off(g) + (uint32_t)(LEAD + lt * 128) * 16u, PANEL_BYTES, 128);
+                    if (!g_stream[g]) continue;                     // the pair does not have this group
+                    const bool mine = g_issue[g];                   // otherwise: walk and release the stages only
+                    const bool split = g_split[g];
+                    const uint32_t tmem_d = g_tmem[g];
+                    const uint64_t a_desc = g_adesc[g];
+                    const int panel16 = g_panel16[g];
                     if (mine) {
-                        mbar_wait_spin<false>(bar_act(g, lt), apar);    // the layer's input rows (own, neighbours', peer's) are in place
+                        // the layer's input rows are in place: this CTA's (own rows, row neighbours', the peer's halo) and
+                        // the peer's (forwarded arrive)
+                        mbar_wait_spin<false>(g_act[g], apar);
                         tc_fence_after();
                     }
                     if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0 && layer < 16) dbg[(16 * g + layer) * 4 + 0] = clock64();
-                    // accumulator := BN shift (constant rows x bias block); starts the layer's accumulation
+                    // accumulator := BN shift (constant rows x bias block); starts the layer's accumulation (split K: in the
+                    // first thread's accumulator; conv_input is not split)
+                    const bool first = !split || lt == 0;
                     next_stage();
-                    if (issue) umma_bf16(tmem_d, bias_a, b_st, IDESC, 0u);
-                    if (leader) umma_commit(bar_empty + 8 * stage);
+                    if (mine && first && leader) umma_bf16_2sm(tmem_d, bias_a, b_st, IDESC, 0u);
+                    if (leader) release_stage();
                     advance();
                     if (layer < 0) {
-                        // conv_input: block j of stage s is tap 4s+j, K = 16 (channel panels 0,1)
+                        // conv_input: block j of stage s is tap 8s+j, K = 16 (channel panels 0,1)
 #pragma unroll
                         for (int s = 0; s < IN_STAGES; s++) {
                             next_stage();
-                            if (issue) {
+                            if (mine && first && leader) {
 #pragma unroll
-                                for (int j = 0; j < 4; j++) {
-                                    const int tap = 4 * s + j;
+                                for (int j = 0; j < STAGE_BLOCKS; j++) {
+                                    const int tap = STAGE_BLOCKS * s + j;
                                     if (tap < 9)
-                                        umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)((tap / 3 - 1) * 10 + (tap % 3 - 1)),
-                                                  b_st + (uint64_t)(j * 256), IDESC, 1u);
+                                        umma_bf16_2sm(tmem_d, a_desc + (uint64_t)(int64_t)((tap / 3 - 1) * 10 + (tap % 3 - 1)),
+                                                      b_st + (uint64_t)(j * 128), IDESC, 1u);
                                 }
                             }
                             if (leader) {
-                                umma_commit(bar_empty + 8 * stage);
-                                if (mine && s == IN_STAGES - 1) {
-                                    umma_commit(bar_accum(g, lt));
-                                    if (signal_peer) umma_commit_mcast(bar_bnd(g), (uint16_t)(1u << peer));
-                                }
+                                release_stage();
+                                if (mine && s == IN_STAGES - 1) umma_commit_2sm(g_accum[g], (uint16_t)3);
                             }
                             advance();
                         }
                     } else {
-                        // stage s holds K-blocks 4s .. 4s+3 in the order of tcx::kblock_of
+                        // stage s holds K-blocks 8s .. 8s+7 in the order of tcx::kblock_of; split K: even stages belong to
+                        // issuer 0, odd stages to issuer 1 (whose first MMA of the layer overwrites its accumulator)
 #pragma unroll
                         for (int s = 0; s < STAGES_PER_LAYER; s++) {
                             next_stage();
-                            if (issue) {
+                            if (mine && leader && (!split || (s & 1) == lt)) {
 #pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    const int m = 4 * s + ks, q = m / 18, rr = m % 18, tap = rr >> 1, unit = q + 4 * (rr & 1);
+                                for (int ks = 0; ks < STAGE_BLOCKS; ks++) {
+                                    const int m = STAGE_BLOCKS * s + ks, q = m / 18, rr = m % 18, tap = rr >> 1, unit = q + 4 * (rr & 1);
                                     const int off = (tap / 3 - 1) * 10 + (tap % 3 - 1) + 2 * unit * panel16;
-                                    umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)off, b_st + (uint64_t)(ks * 256), IDESC, 1u);
+                                    umma_bf16_2sm(tmem_d, a_desc + (uint64_t)(int64_t)off, b_st + (uint64_t)(ks * 128), IDESC,
+                                                  (split && s == 1 && ks == 0) ? 0u : 1u);
                                 }
                             }
                             if (leader) {
-                                umma_commit(bar_empty + 8 * stage);
+                                release_stage();
                                 if (mine && s == STAGES_PER_LAYER - 1) {
-                                    umma_commit(bar_accum(g, lt));
-                                    if (signal_peer) umma_commit_mcast(bar_bnd(g), (uint16_t)(1u << peer));
+                                    umma_commit_2sm(g_accum[g], (uint16_t)3);
                                     if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && layer < 16) dbg[(16 * g + layer) * 4 + 1] = clock64();
                                 }
                             }
@@ -455,11 +537,26 @@ trunk_pp_kernel(const __nv_bfloat16* __restrict__ wq,        // [32][72 K-blocks
     __syncthreads();
     cluster_sync_all();                 // nobody exits while the peer may still write its margins / barriers
     if (warp == EPI_WARPS + 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
 }  // namespace pp
+
+// [block][2 k-panels][128 co][8] -> [stage][cta rank][block of the stage][2 k-panels][64 co][8]: each CTA of a pair holds the
+// output channels 64*rank .. 64*rank+63 of the B operand, and its share of a weight stage is one contiguous bulk copy
+__global__ void split_weights_2sm_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int n_blocks, int bps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;               // one 16-byte (co, 8 ci) unit
+    if (i >= n_blocks * 256) return;
+    int b = i >> 8, pnl = (i >> 7) & 1, co = i & 127;
+    int stage = b / bps, j = b - stage * bps, r = co >> 6;
+    dst[((((size_t)stage * 2 + r) * bps + j) * 2 + pnl) * 64 + (co & 63)] = src[i];
+}
+cudaError_t launch_split_weights_2sm(const __nv_bfloat16* src, __nv_bfloat16* dst, int n_blocks, int blocks_per_stage, cudaStream_t s) {
+    split_weights_2sm_kernel<<<(n_blocks * 256 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const uint4*>(src),
+                                                                             reinterpret_cast<uint4*>(dst), n_blocks, blocks_per_stage);
+    return cudaGetLastError();
+}
 
 cudaError_t trunk_pp_init() {
     cudaError_t e = cudaFuncSetAttribute(pp::trunk_pp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, pp::Cfg<1>::SMEM_BYTES);
@@ -476,12 +573,12 @@ cudaError_t launch_trunk_pp(const NetWeights& w, const __nv_bfloat16* planes, fl
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
     const int cap1 = (n_sm / 2) * (pp::Cfg<1>::MAX_PA + pp::Cfg<1>::MAX_PB);
     pp::trunk_pp_kernel<1><<<2 * pairs, pp::THREADS, pp::Cfg<1>::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.conv_in_w_bf16, w.bias_blk, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, min_count,
+        w.res_w_2sm, w.conv_in_w_2sm, w.bias_blk_2sm, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, min_count,
         cap1, dbg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || max_rows <= cap1) return e;
     pp::trunk_pp_kernel<2><<<2 * pairs, pp::THREADS, pp::Cfg<2>::SMEM_BYTES, s>>>(
-        w.res_w_bf16, w.conv_in_w_bf16, w.bias_blk, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, cap1,
+        w.res_w_2sm, w.conv_in_w_2sm, w.bias_blk_2sm, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, cap1,
         0x7FFFFFFF, dbg);
     return cudaGetLastError();
 }

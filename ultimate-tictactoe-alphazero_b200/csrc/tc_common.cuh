@@ -99,17 +99,20 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
         }
     }
 }
-// Polling wait for the waits on the critical path of a layer (issuer <- epilogue chunk, epilogue <- accumulator): a
-// suspended try_wait wakes up about a thousand cycles after the phase completes, test_wait sees it at once.
-template <bool CLUSTER>
+// Lean wait for the waits on the critical path of a layer (issuer <- epilogue chunk, epilogue <- accumulator): no
+// back-off sleep and no message.  POLL = false suspends in try_wait (the hardware parks the warp for a time slice: a
+// dozen warps waiting this way cost no issue slots); POLL = true spins on test_wait -- lowest wake-up latency, but 16
+// epilogue warps spinning through a whole MMA phase starve the single issuer thread (measured in net_pp.cu: every
+// instruction of the issuer took 200-500 cycles), so it is reserved for short waits of single warps.
+template <bool POLL>
 __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 28); it++) {
-        if (CLUSTER)
+    for (uint32_t it = 0; it < (1u << 26); it++) {
+        if (POLL)
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
-                "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                 "selp.u32 %0, 1, 0, p;\n\t}"
                 : "=r"(ok)
                 : "r"(bar), "r"(parity)
@@ -117,7 +120,7 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
         else
             asm volatile(
                 "{\n\t.reg .pred p;\n\t"
-                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                 "selp.u32 %0, 1, 0, p;\n\t}"
                 : "=r"(ok)
                 : "r"(bar), "r"(parity)
@@ -161,6 +164,26 @@ __device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                  "h"(mask)
                  : "memory");
+}
+// cta_group::2: one MMA of M = 256 over the CTA pair (128 rows from each CTA's shared memory at the same offsets, the B
+// operand split by N between the two CTAs); issued by the leader CTA only
+constexpr uint32_t IDESC_M256_N128_BF16 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(mask)
+                 : "memory");
+}
+// arrive on a barrier of another CTA of the cluster with CTA-scope semantics (one SYNCS.ARRIVE.RED, no MEMBAR.GPU)
+__device__ __forceinline__ void mbar_arrive_peer(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     uint32_t* r = reinterpret_cast<uint32_t*>(v);
