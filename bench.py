@@ -207,7 +207,7 @@ def main():
         sampler.start()
     t_wall0 = time.perf_counter()
     dev_ms, plies, sims, evals, rounds = 0.0, 0, 0, 0, 0
-    trunk_ms, trunk_launches, all_launches, tree_ms, heads_ms = 0.0, 0, 0, 0.0, 0.0
+    trunk_ms, trunk_launches, all_launches = 0.0, 0, 0
     for i in range(args.steps):
         flush.fill_(i & 0xFF)                      # evict L2 between timed steps (not timed)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -219,10 +219,18 @@ def main():
         plies += int(st[0]); sims += int(st[1]); evals += int(st[2]); rounds += int(st[3])
         prof = eng.last_run_profile()
         trunk_ms += prof["trunk"][0]; trunk_launches += prof["trunk"][1]; all_launches += prof["all"][1]
-        tree_ms += prof["tree"][0]; heads_ms += prof["heads"][0]
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
+    # diagnostic, outside the timed region: one more cycle with every kernel bracketed by events (level 2 costs ~1.5 %
+    # of a cycle in GPU idle time at the extra event boundaries, which is why the timed steps only bracket the trunk)
+    eng.set_profile_level(2)
+    st = step(2000)
+    torch.cuda.synchronize()
+    prof = eng.last_run_profile()
+    split = {"tree_kernels": prof["tree"][0], "trunk": prof["trunk"][0], "heads": prof["heads"][0],
+             "device_total": prof["all"][0], "rounds": int(st[3])}
+    eng.set_profile_level(1)
 
     # ---------------- end-to-end through the public host API (H2D weights, D2H history inside the timed region)
     hist = engine.History(args.games)
@@ -289,7 +297,8 @@ def main():
                     "d2h_bytes_per_step": int(hist.nbytes)},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "tensor",
-                         "kernel": "trunk_tc2_kernel / trunk_tc_kernel (one per round, chosen on the device by batch size)"
+                         "kernel": "trunk_auto_kernel (one launch per round; on the device: trunk_tc2_body<2> up to 370 positions, "
+                                   "trunk_pp_body<1> with cta_group::2 MMAs above)"
                          if args.numerics == "bf16" else "conv3x3_fp32_kernel",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None,
@@ -300,8 +309,9 @@ def main():
                          "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                          "flop_per_launch": evals * TRUNK_FLOP_PER_POSITION / max(trunk_launches, 1),
                          "avg_launch_ms": trunk_ms / max(trunk_launches, 1), "launches": trunk_launches},
-            "breakdown_ms_rank0": {"tree_kernels": tree_ms, "trunk": trunk_ms, "heads": heads_ms, "device_total": dev_ms,
-                                   "rounds": rounds, "evals": evals, "plies": plies},
+            "breakdown_ms_rank0": {"trunk": trunk_ms, "tree_heads_and_gaps": dev_ms - trunk_ms, "device_total": dev_ms,
+                                   "rounds": rounds, "evals": evals, "plies": plies,
+                                   "one_extra_cycle_with_all_kernels_timed": split},
             "wall_s": wall_max,
             "saturated": sat,
         }

@@ -120,6 +120,18 @@ typedef struct {
 /* folds BatchNorm, repacks to the tensor-core layouts; synchronous */
 int uttt_upload_weights(uttt_engine *e, const uttt_weights *w, int on_device);
 
+/* The same upload straight from a state_dict (torch.load('./model/best.pth'), self_play_cpp.py:110-112): the 32
+ * residual convolutions `residual_blocks.{b}.conv{1,2}.weight` (index 2*b + j, each (128,128,3,3)) and their
+ * BatchNorm vectors `residual_blocks.{b}.bn{1,2}.{weight,bias,running_mean,running_var}` (128 each) are read from
+ * the caller's 160 tensors where they lie (pinned host memory -> one DMA each, no host-side concatenation);
+ * `small` holds the remaining 12 arrays as in uttt_weights (its res_conv_w / res_bn are ignored).              */
+typedef struct {
+    uttt_weights small;
+    const float *res_conv_w[32];
+    const float *res_bn[32][4];
+} uttt_weights_scattered;
+int uttt_upload_weights_scattered(uttt_engine *e, const uttt_weights_scattered *w, int on_device);
+
 /* DualNetwork.forward on n packed states (dual_network.py:89-121 behind pv_mcts_cpp.py:37-78):
  * policy[n][81] (softmax over all 81 actions), value[n].  mode = UTTT_EVAL_NET_BF16 / _FP32. */
 int uttt_net_forward(uttt_engine *e, const uint32_t *states_dev, int64_t n, int mode,
@@ -178,6 +190,11 @@ int uttt_selfplay_fetch(uttt_engine *e, int64_t n_games, uint32_t *hist_states, 
 /* timing of the engine's own kernels during the last uttt_selfplay_run*: CUDA-event ms on the
  * launching stream and launch counts; kind: 0 tree kernels, 1 trunk, 2 heads, 3 everything */
 int uttt_last_run_profile(uttt_engine *e, int kind, double *ms_out, int64_t *launches_out);
+
+/* which of those kernels are bracketed by CUDA events during self-play (an event between two dependent kernels costs
+ * about 1 us of GPU idle time): 0 none, 1 the trunk only (default: what the roofline needs), 2 tree / trunk / heads
+ * (kind 0, 2, 3 of uttt_last_run_profile report 0 ms below level 2).  Launch counts are always kept. */
+int uttt_set_profile_level(uttt_engine *e, int level);
 
 /* diagnostics: clock64 timeline of CTA 0 of the last tensor-core trunk launch, [32 layers][4]:
  * MMA start, MMA issue done, accumulators ready (epilogue start), epilogue done */

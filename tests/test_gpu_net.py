@@ -249,8 +249,8 @@ def test_fp32_trunk_vs_reference_golden_outputs(setup, golden_dir):
 
 def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
     """The trunk kernel is chosen on the device from the batch size and the group sizes from ceil(n / pairs): every
-    boundary of that dispatch must produce the same rows.  Default (UTTT_TRUNK=3): one group per CTA pair up to 370
-    positions (net_tc2.cu), two groups in flight above (net_pp.cu, cta_group::2).  All of them accumulate a row in the
+    boundary of that dispatch must produce the same rows.  Default (UTTT_TRUNK=4, one launch that branches on the device,
+    net_auto.cu): one group per CTA pair up to 370 positions (net_tc2), two groups in flight above (net_pp, cta_group::2).  All of them accumulate a row in the
     same order -- bit-identical -- except the one-tile group of the 6/7-positions-per-pair case (371..518 positions),
     whose K loop is split over two accumulators: fp32 re-association, checked on a well-conditioned network."""
     import copy
@@ -282,8 +282,32 @@ def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
         ref_p, ref_v = _forward(e3, big[:800], engine.EVAL_NET_BF16)
         f32_p, _ = _forward(e3, big[:64], engine.EVAL_NET_FP32)
         assert (ref_p[:64].argmax(1) == f32_p.argmax(1)).mean() > 0.9
+        same_n = (1, 2, 3, 7, 8, 74, 75, 149, 223, 300, 370, 371, 444, 445, 500, 518, 519, 800)
+        ref_n = {n: _forward(e3, big[:n], engine.EVAL_NET_BF16) for n in same_n}
     finally:
         e3.close()
+    # an engine whose batches cannot exceed one group per CTA pair (<= 518 rows: the 500-game cycle) runs the heads' FC
+    # layers in the tail of the trunk kernel; e3 above (1600 rows) ran them as a separate kernel: same bits
+    for rows in (518, 500, 8):
+        ef = engine.Engine(n_slots=rows, max_sims=50, max_batch=8, max_games=8)
+        try:
+            ef.upload_model(model)
+            for n in same_n:
+                if n <= rows:
+                    p, v = _forward(ef, big[:n], engine.EVAL_NET_BF16)
+                    assert (p == ref_n[n][0]).all() and (v == ref_n[n][1]).all(), (rows, n)
+        finally:
+            ef.close()
+    # UTTT_TRUNK=3: the same two kernels as separate launches (each exits if the batch is not in its range)
+    monkeypatch.setenv("UTTT_TRUNK", "3")
+    ev = engine.Engine(n_slots=800, max_sims=50, max_batch=8, max_games=8)
+    try:
+        ev.upload_model(model)
+        for n in same_n:
+            p, v = _forward(ev, big[:n], engine.EVAL_NET_BF16)
+            assert (p == ref_n[n][0]).all() and (v == ref_n[n][1]).all(), n
+    finally:
+        ev.close()
     # the earlier kernel families stay selectable: UTTT_TRUNK=2 (CTA pairs with 2 or 3 tiles per CTA up to 518 positions,
     # one CTA per group above), UTTT_TRUNK=1 (one CTA per group only).  The one-CTA kernel sums the heads' 1x1 convs in
     # another order (whole row vs two column halves): ~1e-5 on the ill-conditioned random-init net
@@ -300,3 +324,30 @@ def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
                     assert np.abs(p - ref_p[:n]).max() < 1e-3 and np.abs(v - ref_v[:n]).max() < 1e-3, (variant, n)
         finally:
             ev.close()
+
+
+def test_state_dict_upload_paths_give_identical_networks(setup):
+    """uttt_upload_weights_scattered (contiguous host tensors read where they lie) == uttt_upload_weights (one packed
+    host copy; taken for device-resident / non-contiguous / non-fp32 state_dicts) == device pointers"""
+    import torch
+    import engine
+    e, model, sts = setup
+    sd = {k: v.clone() for k, v in _damped(type(model)().eval()).state_dict().items()}
+    assert engine.scattered_residual_tensors(sd) is not None
+    e.upload_state_dict(sd)
+    p0, v0 = _forward(e, sts[:300], engine.EVAL_NET_BF16)
+    q0, w0 = _forward(e, sts[:64], engine.EVAL_NET_FP32)
+    pinned = {k: v.pin_memory() for k, v in sd.items()}
+    halves = {k: v.double() for k, v in sd.items()}                  # wrong dtype -> packed path (converted to fp32)
+    on_gpu = {k: v.cuda() for k, v in sd.items()}                    # device tensors -> packed path
+    assert engine.scattered_residual_tensors(halves) is None and engine.scattered_residual_tensors(on_gpu) is None
+    for other in (pinned, halves, on_gpu):
+        e.upload_state_dict({k: torch.zeros_like(v) for k, v in sd.items()})       # really replaced in between
+        e.upload_state_dict(other)
+        p, v = _forward(e, sts[:300], engine.EVAL_NET_BF16)
+        q, w = _forward(e, sts[:64], engine.EVAL_NET_FP32)
+        assert (p == p0).all() and (v == v0).all() and (q == q0).all() and (w == w0).all()
+    bad = dict(sd)
+    bad["residual_blocks.3.conv2.weight"] = torch.zeros(128, 64, 3, 3)
+    with pytest.raises(ValueError):
+        e.upload_state_dict(bad)

@@ -6,7 +6,7 @@ import numpy as np, torch, engine, oracle_lib as O
 from dual_network import DualNetwork
 n = int(sys.argv[1]); reps = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 torch.manual_seed(0)
-e = engine.Engine(n_slots=max(n, 8), max_sims=50, max_batch=8, max_games=8)
+e = engine.Engine(n_slots=max(n, int(os.environ.get("FWD_SLOTS", "8"))), max_sims=50, max_batch=8, max_games=8)
 e.upload_model(DualNetwork().eval())
 sts = np.concatenate([O.playout_states(1, g)[0][:-1] for g in range(n // 40 + 2)])[:n]
 d = torch.from_numpy(sts.view(np.int32)).cuda()

@@ -128,6 +128,7 @@ struct NetWeights {
     // heads (fp32): policy conv [2][128] + shift[2], fc [81][162] + b; value conv [128] + shift, fc1 [256][81]+b, fc2 [256]+b
     float* pol_conv_w; float* pol_conv_b; float* pol_fc_w; float* pol_fc_b;
     float* val_conv_w; float* val_conv_b; float* val_fc1_w; float* val_fc1_b; float* val_fc2_w; float* val_fc2_b;
+    float* heads_pack;      // policy_fc / value_fc1 weights in the chunk order of heads_fc.cuh (bulk-copied to shared memory)
     bool loaded;
 };
 
@@ -159,6 +160,14 @@ cudaError_t launch_split_weights_2sm(const __nv_bfloat16* src, __nv_bfloat16* ds
 cudaError_t launch_trunk_pp(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count, int max_rows,
                             float* skip, int n_sm, cudaStream_t s, long long* dbg, int min_count);
 cudaError_t trunk_pp_init();
+int trunk_pp_cap1(int n_sm);         // largest batch of the 7-positions-per-pair instantiation
+cudaError_t launch_trunk_pp_large(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
+                                  int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg);
+// one launch for every batch up to trunk_pp_cap1: device-side choice between trunk_tc2_kernel<2> and trunk_pp_kernel<1>
+// (policy / value non-null: the heads' FC layers run in the kernel's tail; requires max_rows <= trunk_pp_cap1)
+cudaError_t launch_trunk_auto(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count, int max_rows,
+                              float* skip, int n_sm, cudaStream_t s, long long* dbg, float* policy, float* value);
+cudaError_t trunk_auto_init();
 int trunk_tc2_capacity(int n_sm);    // largest batch the cluster variant evaluates in one wave
 int trunk_tc_smem_bytes();
 cudaError_t trunk_tc_init();

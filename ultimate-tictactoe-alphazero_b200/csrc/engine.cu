@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "heads_fc.cuh"
 
 using namespace uttt;
 
@@ -25,7 +26,8 @@ namespace {
 
 constexpr int CHECK_EVERY = 16;
 constexpr int N_LANES = 2;
-constexpr int EV_POOL = CHECK_EVERY * 4 * N_LANES;
+constexpr int N_WINDOWS = 2;           // self-play keeps two windows of CHECK_EVERY rounds in flight
+constexpr int EV_POOL = N_WINDOWS * CHECK_EVERY * 4 * N_LANES;
 
 __global__ void set_int_kernel(int32_t* p, int32_t v) { *p = v; }
 
@@ -65,7 +67,7 @@ struct uttt_engine {
     int rows_per_slot;      // evaluator rows per slot (max_batch: throughput mode queues up to that many leaves)
     cudaStream_t stream;
     cudaStream_t lane_stream[N_LANES];
-    cudaEvent_t ev_fork, ev_join[N_LANES];
+    cudaEvent_t ev_fork, ev_join[N_LANES], ev_win[N_WINDOWS][N_LANES];
     TreeParams tp;          // device pointers (n_trees / mode / sims set per call)
     float* policy;          // [n_slots*max_batch][81]
     float* value;           // [n_slots*max_batch]
@@ -76,14 +78,16 @@ struct uttt_engine {
     float* tc_resid;        // [n_sm][32][512][4] fp32 residual stream of the tensor-core trunk (per CTA)
     int32_t* fwd_count;     // device int for uttt_net_forward
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0, then [64] histogram of batch sizes (diagnostics)
+    int prof_level;         // self-play kernel timing: 2 = tree / trunk / heads events every round, 1 = trunk only, 0 = none
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
-    int trunk_variant;      // 3 (default): CTA pair per group (net_tc2.cu) up to 370 positions, two groups in flight per pair with
-                            // cta_group::2 MMAs (net_pp.cu) above; for comparison 2: net_tc2.cu (2 or 3 tiles per CTA) up to 518
-                            // positions and net_tc.cu above, 1: one CTA per group (net_tc.cu) only
+    int trunk_variant;      // 4 (default): CTA pair per group (net_tc2) up to 370 positions, two groups in flight per pair with
+                            // cta_group::2 MMAs (net_pp) above, chosen on the device inside ONE launch (net_auto.cu); 3: the
+                            // same two kernels as separate launches; for comparison 2: net_tc2 (2 or 3 tiles per CTA) up to
+                            // 518 positions and net_tc above, 1: one CTA per group (net_tc) only
     NetWeights w;
     float* raw_res;         // staging for the raw residual conv weights / bn of an upload
     float* raw_res_bn;
-    unsigned long long* h_counters;   // pinned [8]
+    unsigned long long* h_counters;   // pinned [8 * (1 + N_WINDOWS)]: [0..7] general use, then one copy per self-play window
     int32_t* h_count;                 // pinned [2]
     // step-wise search state
     int s_n_roots, s_sims, s_batch, s_round, s_pending, s_per_copy, s_have_results;
@@ -136,6 +140,7 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         return 0;
     }
     UTTT_CHECK(e->w.loaded, "network weights not uploaded (uttt_upload_weights)");
+    bool heads_fused = false;
     if (evaluator == UTTT_EVAL_NET_FP32) {
         if (ev3) cudaEventRecord(ev3[0], s);
         UTTT_CUDA_OK(launch_trunk_fp32(e->w, b.nn_planes, count, max_rows, b.act_a, b.act_b, s));
@@ -146,7 +151,16 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         // (one wave of CTA pairs) are latency-bound -> cluster variant, larger ones are throughput-bound -> one CTA
         // per group with 4 accumulator tiles.  Counted as ONE trunk launch per round.
         if (ev3) cudaEventRecord(ev3[0], s);
-        if (e->trunk_variant == 3) {
+        if (e->trunk_variant == 4) {
+            // one launch: the kernel branches on the queue length (net_auto.cu); batches above 7 positions per CTA pair
+            // (only possible when max_rows allows them) are left to the 10-positions-per-pair instantiation
+            // (if no batch can exceed one group per pair, the heads' FC layers run in the tail of the same kernel)
+            heads_fused = max_rows <= trunk_pp_cap1(e->n_sm);
+            UTTT_CUDA_OK(launch_trunk_auto(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
+                                           heads_fused ? b.policy : nullptr, heads_fused ? b.value : nullptr));
+            if (!heads_fused)
+                UTTT_CUDA_OK(launch_trunk_pp_large(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+        } else if (e->trunk_variant == 3) {
             // up to one wave of 5-position groups: cluster kernel whose next layer overlaps the epilogue; above: the
             // two-groups-in-flight kernel (net_pp.cu)
             const int cap = trunk_tc2_small_capacity(e->n_sm);
@@ -166,12 +180,16 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         UTTT_CHECK(false, "evaluator %d cannot run on the device", evaluator);
     }
     if (ev3) cudaEventRecord(ev3[1], s);
+    if (heads_fused) {
+        if (ev3 && e->prof_level >= 2) cudaEventRecord(ev3[2], s);
+        return 0;
+    }
     if (evaluator == UTTT_EVAL_NET_BF16)
         UTTT_CUDA_OK(launch_heads_fc(e->w, b.headfeat, count, max_rows, b.policy, b.value, 1, s));
     else
         UTTT_CUDA_OK(launch_heads(e->w, b.act_a, nullptr, count, max_rows, b.policy, b.value, 1, s));
     e->prof_launches[2] += 1;
-    if (ev3) cudaEventRecord(ev3[2], s);
+    if (ev3 && e->prof_level >= 2) cudaEventRecord(ev3[2], s);
     return 0;
 }
 
@@ -199,7 +217,8 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     memset(&e->tp, 0, sizeof(e->tp));
     memset(&e->w, 0, sizeof(e->w));
     e->cfg = *cfg;
-    e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 3;
+    e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 4;
+    e->prof_level = getenv("UTTT_PROFILE") ? atoi(getenv("UTTT_PROFILE")) : 1;
     e->lane_threshold = getenv("UTTT_LANE_THRESHOLD") ? atoi(getenv("UTTT_LANE_THRESHOLD")) : 1024;
     cudaDeviceProp prop;
     UTTT_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -231,9 +250,10 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     for (int i = 0; i < N_LANES; i++) {
         UTTT_CUDA_OK(cudaStreamCreateWithFlags(&e->lane_stream[i], cudaStreamNonBlocking));
         UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming));
+        for (int w = 0; w < N_WINDOWS; w++) UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_win[w][i], cudaEventDisableTiming));
     }
     UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-    UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_counters, 8 * sizeof(unsigned long long)));
+    UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_counters, 8 * (1 + N_WINDOWS) * sizeof(unsigned long long)));
     UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_count, 2 * sizeof(int32_t)));
     for (int i = 0; i < EV_POOL; i++) UTTT_CUDA_OK(cudaEventCreate(&e->ev[i]));
     t.policy = e->policy;
@@ -251,7 +271,7 @@ int uttt_destroy(uttt_engine* e) {
     for (void* p : e->allocs) cudaFree(p);
     float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, e->w.head_w, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
-                   e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b};
+                   e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b, e->w.heads_pack};
     for (float* p : wp) if (p) cudaFree(p);
     if (e->raw_res) cudaFree(e->raw_res);
     if (e->raw_res_bn) cudaFree(e->raw_res_bn);
@@ -262,6 +282,7 @@ int uttt_destroy(uttt_engine* e) {
     for (int i = 0; i < N_LANES; i++) {
         if (e->lane_stream[i]) cudaStreamDestroy(e->lane_stream[i]);
         if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+        for (int w = 0; w < N_WINDOWS; w++) if (e->ev_win[w][i]) cudaEventDestroy(e->ev_win[w][i]);
     }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
     delete e;
@@ -286,7 +307,10 @@ static int to_device(float** dst, const std::vector<float>& v) {
     return 0;
 }
 
-int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
+// res_tab / res_bn_tab (optional): the 32 residual convolutions and their 32 x 4 BatchNorm vectors as separate tensors
+// (state_dict entries copied straight from the caller's memory, no host-side concatenation)
+static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, const float* const* res_tab,
+                       const float* const (*res_bn_tab)[4]) {
     UTTT_CHECK(e && w, "null argument");
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     auto fetch = [&](const float* p, size_t n, std::vector<float>& v) -> int {
@@ -303,7 +327,7 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
         fetch(w->value_fc1_w, 256 * 81, v1w) || fetch(w->value_fc1_b, 256, v1b) || fetch(w->value_fc2_w, 256, v2w) ||
         fetch(w->value_fc2_b, 1, v2b))
         return 1;
-    UTTT_CHECK(w->res_conv_w && w->res_bn, "null weight tensor");
+    UTTT_CHECK(res_tab || (w->res_conv_w && w->res_bn), "null weight tensor");
 
     // the 32 residual convolutions (4.7 M weights) are folded and repacked by a kernel
     const size_t n_res = (size_t)32 * 128 * 128 * 9, n_rbn = (size_t)32 * 4 * 128;
@@ -316,8 +340,20 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
         UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_bf16, n_res * sizeof(__nv_bfloat16)));
     }
     cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res, w->res_conv_w, n_res * sizeof(float), kind, e->stream));
-    UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res_bn, w->res_bn, n_rbn * sizeof(float), kind, e->stream));
+    if (res_tab) {
+        const size_t per = (size_t)128 * 128 * 9;
+        for (int l = 0; l < 32; l++) {
+            UTTT_CHECK(res_tab[l] != nullptr, "null weight tensor");
+            UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res + l * per, res_tab[l], per * sizeof(float), kind, e->stream));
+            for (int j = 0; j < 4; j++) {
+                UTTT_CHECK(res_bn_tab[l][j] != nullptr, "null weight tensor");
+                UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res_bn + (l * 4 + j) * 128, res_bn_tab[l][j], 128 * sizeof(float), kind, e->stream));
+            }
+        }
+    } else {
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res, w->res_conv_w, n_res * sizeof(float), kind, e->stream));
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res_bn, w->res_bn, n_rbn * sizeof(float), kind, e->stream));
+    }
     pack_res_kernel<<<ceil_div((int64_t)n_res, 256), 256, 0, e->stream>>>(e->raw_res, e->raw_res_bn, W.res_w, W.res_b,
                                                                          W.res_w_bf16);
     UTTT_CUDA_OK(cudaGetLastError());
@@ -391,6 +427,21 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
         hw[384] = pc_b[0]; hw[385] = pc_b[1]; hw[386] = vc_b[0];
         if (to_device(&W.head_w, hw)) return 1;
     }
+    {
+        // FC weights of the heads in the order heads_fc_block streams them: 3 chunks of 27 input rows
+        std::vector<float> pack(HEADS_PACK_FLOATS, 0.0f);
+        for (int c = 0; c < HEADS_CHUNKS; c++) {
+            float* dst = pack.data() + (size_t)c * HEADS_CHUNK_FLOATS;
+            for (int h = 0; h < 2; h++)
+                for (int i = 0; i < HEADS_CHUNK_ROWS; i++)
+                    for (int o = 0; o < 81; o++)
+                        dst[h * HEADS_POL_FLOATS + i * 81 + o] = pf_t[(size_t)(h * 81 + c * HEADS_CHUNK_ROWS + i) * 81 + o];
+            for (int i = 0; i < HEADS_CHUNK_ROWS; i++)
+                for (int j = 0; j < 256; j++)
+                    dst[2 * HEADS_POL_FLOATS + i * 256 + j] = v1_t[(size_t)(c * HEADS_CHUNK_ROWS + i) * 256 + j];
+        }
+        if (to_device(&W.heads_pack, pack)) return 1;
+    }
     if (to_device(&W.conv_in_w, ci_w) || to_device(&W.conv_in_b, ci_b) || to_device(&W.pol_conv_w, pc_w) || to_device(&W.pol_conv_b, pc_b) ||
         to_device(&W.pol_fc_w, pf_t) || to_device(&W.pol_fc_b, pfb) || to_device(&W.val_conv_w, vc_w) ||
         to_device(&W.val_conv_b, vc_b) || to_device(&W.val_fc1_w, v1_t) || to_device(&W.val_fc1_b, v1b) ||
@@ -400,8 +451,18 @@ int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
     UTTT_CUDA_OK(trunk_tc_init());
     UTTT_CUDA_OK(trunk_tc2_init());
     UTTT_CUDA_OK(trunk_pp_init());
+    UTTT_CUDA_OK(trunk_auto_init());
     W.loaded = true;
     return 0;
+}
+
+int uttt_upload_weights(uttt_engine* e, const uttt_weights* w, int on_device) {
+    return upload_impl(e, w, on_device, nullptr, nullptr);
+}
+
+int uttt_upload_weights_scattered(uttt_engine* e, const uttt_weights_scattered* w, int on_device) {
+    UTTT_CHECK(e && w, "null argument");
+    return upload_impl(e, &w->small, on_device, w->res_conv_w, w->res_bn);
 }
 
 int uttt_net_forward(uttt_engine* e, const uint32_t* states_dev, int64_t n, int mode, float* policy_dev,
@@ -625,37 +686,65 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     int64_t max_rounds = waves * 82 * (int64_t)(sims + 3) * (tp ? 4 : 1) + CHECK_EVERY;
     int64_t r = 0;
     bool done = false;
-    while (!done && r < max_rounds) {
-        int in_window = 0;
-        for (; in_window < CHECK_EVERY; in_window++, r++) {
+    // Two windows of CHECK_EVERY rounds are kept in flight: window w+1 is enqueued before the host waits for window w,
+    // so the GPU never idles while the host reads the progress counters and the per-kernel event times (one window at
+    // a time, that wait cost ~230 us of GPU idle time per window = 4 % of a 500-game cycle).  The price is up to one
+    // extra window of rounds after the last game ended (every kernel of such a round exits at once).
+    auto enqueue_window = [&](int slot) -> int {
+        for (int i = 0; i < CHECK_EVERY; i++, r++) {
             for (int l = 0; l < n_lanes; l++) {
-                cudaEvent_t* ev = e->ev + 4 * (in_window * N_LANES + l);
+                cudaEvent_t* ev = e->ev + 4 * ((slot * CHECK_EVERY + i) * N_LANES + l);
                 lane_tp[l].parity = (int)(r & 1);
-                cudaEventRecord(ev[0], ls[l]);
+                if (e->prof_level >= 2) cudaEventRecord(ev[0], ls[l]);
                 UTTT_CUDA_OK(tp ? launch_tree_tp_round(lane_tp[l], ls[l]) : launch_tree_round(lane_tp[l], ls[l]));
                 e->prof_launches[0] += 1;
                 if (run_evaluator(e, lane_bufs[l], evaluator, lane_tp[l].nn_count + lane_tp[l].parity,
                                   lane_trees[l] * rows_per_tree,
-                                  ls[l], ev + 1))
+                                  ls[l], e->prof_level >= 1 ? ev + 1 : nullptr))
                     return 1;
             }
         }
-        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                     ls[0]));
-        for (int l = 0; l < n_lanes; l++) UTTT_CUDA_OK(cudaStreamSynchronize(ls[l]));
-        for (int i = 0; i < in_window; i++) {
+        UTTT_CUDA_OK(cudaMemcpyAsync(e->h_counters + 8 * (1 + slot), t.counters, 8 * sizeof(unsigned long long),
+                                     cudaMemcpyDeviceToHost, ls[0]));
+        for (int l = 0; l < n_lanes; l++) UTTT_CUDA_OK(cudaEventRecord(e->ev_win[slot][l], ls[l]));
+        return 0;
+    };
+    auto retire_window = [&](int slot) -> int {
+        for (int l = 0; l < n_lanes; l++) UTTT_CUDA_OK(cudaEventSynchronize(e->ev_win[slot][l]));
+        for (int i = 0; i < CHECK_EVERY; i++) {
             for (int l = 0; l < n_lanes; l++) {
                 float ms = 0.f;
-                cudaEvent_t* ev = e->ev + 4 * (i * N_LANES + l);
-                cudaEventElapsedTime(&ms, ev[0], ev[1]); e->prof_ms[0] += ms;
-                cudaEventElapsedTime(&ms, ev[1], ev[2]); e->prof_ms[1] += ms;
-                cudaEventElapsedTime(&ms, ev[2], ev[3]); e->prof_ms[2] += ms;
-                cudaEventElapsedTime(&ms, ev[0], ev[3]); e->prof_ms[3] += ms;
+                cudaEvent_t* ev = e->ev + 4 * ((slot * CHECK_EVERY + i) * N_LANES + l);
+                if (e->prof_level >= 1) { cudaEventElapsedTime(&ms, ev[1], ev[2]); e->prof_ms[1] += ms; }
+                if (e->prof_level >= 2) {
+                    cudaEventElapsedTime(&ms, ev[0], ev[1]); e->prof_ms[0] += ms;
+                    cudaEventElapsedTime(&ms, ev[2], ev[3]); e->prof_ms[2] += ms;
+                    cudaEventElapsedTime(&ms, ev[0], ev[3]); e->prof_ms[3] += ms;
+                }
             }
         }
-        UTTT_CHECK(e->h_counters[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
+        const unsigned long long* hc = e->h_counters + 8 * (1 + slot);
+        UTTT_CHECK(hc[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
         // lane 0's copy may predate lane 1's last rounds: "done" only ever lags, never leads
-        done = (int64_t)e->h_counters[1] >= n_games;
+        done = (int64_t)hc[1] >= n_games;
+        return 0;
+    };
+    int head = 0, in_flight = 0;                 // windows are retired in the order they were enqueued
+    while (!done && (r < max_rounds || in_flight > 0)) {
+        while (in_flight < N_WINDOWS && r < max_rounds) {
+            if (enqueue_window((head + in_flight) % N_WINDOWS)) return 1;
+            in_flight++;
+        }
+        if (retire_window(head)) return 1;
+        head = (head + 1) % N_WINDOWS;
+        in_flight--;
+    }
+    while (in_flight > 0) {                      // the window enqueued behind the one that saw the last game end
+        bool was_done = done;
+        if (retire_window(head)) return 1;
+        done = done || was_done;
+        head = (head + 1) % N_WINDOWS;
+        in_flight--;
     }
     if (n_lanes > 1) {          // join: the caller's stream continues after both lanes
         for (int l = 0; l < n_lanes; l++) {
@@ -724,6 +813,13 @@ int uttt_debug_batch_histogram(uttt_engine* e, int64_t* out64, int32_t reset) {
     UTTT_CUDA_OK(cudaDeviceSynchronize());
     UTTT_CUDA_OK(cudaMemcpy(out64, e->tc_dbg + 128, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
     if (reset) UTTT_CUDA_OK(cudaMemset(e->tc_dbg + 128, 0, 64 * sizeof(long long)));
+    return 0;
+}
+
+int uttt_set_profile_level(uttt_engine* e, int level) {
+    UTTT_CHECK(e != nullptr, "null engine");
+    UTTT_CHECK(level >= 0 && level <= 2, "profile level %d outside [0, 2]", level);
+    e->prof_level = level;
     return 0;
 }
 

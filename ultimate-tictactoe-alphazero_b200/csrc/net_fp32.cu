@@ -9,6 +9,7 @@
 // Spatial index = picture cell R*9+C (the (3,9,9) planes of cpp/uttt_game.cpp:244-280 after the
 // NHWC->NCHW transpose); channel is the fastest-varying dimension of every activation buffer.
 #include "common.cuh"
+#include "heads_fc.cuh"
 
 namespace uttt {
 
@@ -205,66 +206,28 @@ __global__ void __launch_bounds__(128) heads_kernel(NetWeights W, const float* _
     if (threadIdx.x == 0) value[orow] = tanhf(red[0] + red[1] + red[2] + red[3] + W.val_fc2_b[0]);
 }
 
-// Heads after the tensor-core trunk: the 1x1 convolutions + BN + ReLU were already applied in the trunk's last
-// epilogue (headfeat = [row][243]); this is policy_fc + softmax and value_fc1 + ReLU + value_fc2 + tanh
-// (dual_network.py:106-108,115-119).  One block (128 threads) per position.
-__global__ void __launch_bounds__(128) heads_fc_kernel(NetWeights W, const float* __restrict__ headfeat,
-                                                       const int32_t* __restrict__ count, float* __restrict__ policy,
-                                                       float* __restrict__ value, int row_stride) {
-    int row = blockIdx.x;
-    if (row >= *count) return;
-    __shared__ float f[243];
-    __shared__ float hid[256];
-    __shared__ float red[4];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < 243; i += 128) f[i] = headfeat[(size_t)row * 243 + i];
-    __syncthreads();
-    float lg = -INFINITY;
-    if (threadIdx.x < 81) {
-        float a0 = W.pol_fc_b[threadIdx.x], a1 = 0.0f;
-        for (int i = 0; i < 162; i += 2) {
-            a0 = fmaf(f[i], W.pol_fc_w[i * 81 + threadIdx.x], a0);
-            a1 = fmaf(f[i + 1], W.pol_fc_w[(i + 1) * 81 + threadIdx.x], a1);
-        }
-        lg = a0 + a1;
-    }
-    for (int j = threadIdx.x; j < 256; j += 128) {
-        float a0 = W.val_fc1_b[j], a1 = 0.0f;
-        for (int i = 0; i < 80; i += 2) {
-            a0 = fmaf(f[162 + i], W.val_fc1_w[i * 256 + j], a0);
-            a1 = fmaf(f[163 + i], W.val_fc1_w[(i + 1) * 256 + j], a1);
-        }
-        a0 = fmaf(f[242], W.val_fc1_w[80 * 256 + j], a0);
-        hid[j] = fmaxf(a0 + a1, 0.0f);
-    }
-    float m = lg;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
-    if (lane == 0) red[warp] = m;
-    __syncthreads();
-    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    float e = (threadIdx.x < 81) ? expf(lg - m) : 0.0f;
-    float s = e;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, off);
-    __syncthreads();
-    if (lane == 0) red[warp] = s;
-    __syncthreads();
-    s = red[0] + red[1] + red[2] + red[3];
-    size_t orow = (size_t)row * row_stride;
-    if (threadIdx.x < 81) policy[orow * 81 + threadIdx.x] = e / s;
-    float a = hid[threadIdx.x] * W.val_fc2_w[threadIdx.x] + hid[threadIdx.x + 128] * W.val_fc2_w[threadIdx.x + 128];
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) a += __shfl_xor_sync(0xFFFFFFFFu, a, off);
-    __syncthreads();
-    if (lane == 0) red[warp] = a;
-    __syncthreads();
-    if (threadIdx.x == 0) value[orow] = tanhf(red[0] + red[1] + red[2] + red[3] + W.val_fc2_b[0]);
+// Heads after the tensor-core trunk when they are not fused into its tail (batches of more than one group per CTA
+// pair, the single-CTA trunks, uttt_net_forward on large batches): one block per HEADS_P positions, see heads_fc.cuh.
+__global__ void __launch_bounds__(HEADS_THREADS) heads_fc_kernel(HeadsFC W, const float* __restrict__ headfeat,
+                                                                 const int32_t* __restrict__ count, float* __restrict__ policy,
+                                                                 float* __restrict__ value, int row_stride) {
+    const int row0 = blockIdx.x * HEADS_P;
+    const int n = *count;
+    if (row0 >= n) return;
+    extern __shared__ __align__(16) float heads_sm[];
+    heads_fc_block(W, headfeat, row0, 1, min(HEADS_P, n - row0), policy, value, row_stride, heads_sm);
 }
 
 cudaError_t launch_heads_fc(const NetWeights& w, const float* headfeat, const int32_t* count, int max_rows, float* policy,
                             float* value, int row_stride, cudaStream_t s) {
-    heads_fc_kernel<<<max_rows, 128, 0, s>>>(w, headfeat, count, policy, value, row_stride);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(heads_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADS_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    heads_fc_kernel<<<(max_rows + HEADS_P - 1) / HEADS_P, HEADS_THREADS, HEADS_SMEM_BYTES, s>>>(heads_fc_of(w), headfeat, count, policy,
+                                                                                                 value, row_stride);
     return cudaGetLastError();
 }
 

@@ -36,6 +36,10 @@ class UtttWeights(C.Structure):
     _fields_ = [(n, _vp) for n in _WEIGHT_FIELDS]
 
 
+class UtttWeightsScattered(C.Structure):
+    _fields_ = [("small", UtttWeights), ("res_conv_w", _vp * 32), ("res_bn", (_vp * 4) * 32)]
+
+
 # every symbol include/uttt_b200.h declares: name -> (argtypes, restype)
 ABI = {
     "uttt_last_error": ([], C.c_char_p),
@@ -55,6 +59,7 @@ ABI = {
     "uttt_create": ([C.POINTER(UtttConfig), C.POINTER(_vp)], C.c_int),
     "uttt_destroy": ([_vp], C.c_int),
     "uttt_upload_weights": ([_vp, C.POINTER(UtttWeights), C.c_int], C.c_int),
+    "uttt_upload_weights_scattered": ([_vp, C.POINTER(UtttWeightsScattered), C.c_int], C.c_int),
     "uttt_net_forward": ([_vp, _vp, C.c_int64, C.c_int, _vp, _vp, _vp], C.c_int),
     "uttt_mcts_search": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp],
                          C.c_int),
@@ -73,6 +78,7 @@ ABI = {
     "uttt_debug_trunk_timeline": ([_vp, _vp], C.c_int),
     "uttt_debug_batch_histogram": ([_vp, _vp, C.c_int32], C.c_int),
     "uttt_last_run_profile": ([_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
+    "uttt_set_profile_level": ([_vp, C.c_int], C.c_int),
 }
 
 _lib = None
@@ -166,38 +172,68 @@ def game_playout(seed, game0, n, device="cuda", stream=None):
 
 
 # ------------------------------------------------------------------------------------ weights
-def pack_state_dict(sd):
-    """DualNetwork state_dict (dual_network.py:47-75; 216 entries) -> dict of the 14 contiguous fp32
-    arrays the C ABI takes (numpy, host)."""
-    def a(k):
-        return sd[k].detach().to("cpu").float().numpy()
+_SMALL_SHAPES = {"conv_input_w": (128, 3, 3, 3), "bn_input": (4, 128), "policy_conv_w": (2, 128), "policy_bn": (4, 2),
+                 "policy_fc_w": (81, 162), "policy_fc_b": (81,), "value_conv_w": (1, 128), "value_bn": (4, 1),
+                 "value_fc1_w": (256, 81), "value_fc1_b": (256,), "value_fc2_w": (1, 256), "value_fc2_b": (1,)}
+_BN_KEYS = (".weight", ".bias", ".running_mean", ".running_var")
 
-    def bn(prefix):
-        return np.stack([a(prefix + ".weight"), a(prefix + ".bias"), a(prefix + ".running_mean"),
-                         a(prefix + ".running_var")])
-    n_blocks = 16
-    res_w = np.stack([np.stack([a("residual_blocks.%d.conv1.weight" % i), a("residual_blocks.%d.conv2.weight" % i)])
-                      for i in range(n_blocks)])
-    res_bn = np.stack([np.stack([bn("residual_blocks.%d.bn1" % i), bn("residual_blocks.%d.bn2" % i)])
-                       for i in range(n_blocks)])
-    out = {
-        "conv_input_w": a("conv_input.weight"), "bn_input": bn("bn_input"),
-        "res_conv_w": res_w, "res_bn": res_bn,
-        "policy_conv_w": a("policy_conv.weight").reshape(2, 128), "policy_bn": bn("policy_bn"),
-        "policy_fc_w": a("policy_fc.weight"), "policy_fc_b": a("policy_fc.bias"),
-        "value_conv_w": a("value_conv.weight").reshape(1, 128), "value_bn": bn("value_bn"),
-        "value_fc1_w": a("value_fc1.weight"), "value_fc1_b": a("value_fc1.bias"),
-        "value_fc2_w": a("value_fc2.weight"), "value_fc2_b": a("value_fc2.bias"),
-    }
-    shapes = {"conv_input_w": (128, 3, 3, 3), "bn_input": (4, 128), "res_conv_w": (16, 2, 128, 128, 3, 3),
-              "res_bn": (16, 2, 4, 128), "policy_conv_w": (2, 128), "policy_bn": (4, 2), "policy_fc_w": (81, 162),
-              "policy_fc_b": (81,), "value_conv_w": (1, 128), "value_bn": (4, 1), "value_fc1_w": (256, 81),
-              "value_fc1_b": (256,), "value_fc2_w": (1, 256), "value_fc2_b": (1,)}
+
+def _check_shapes(out, shapes):
     for k, shp in shapes.items():
         out[k] = np.ascontiguousarray(out[k], dtype=np.float32)
         if out[k].shape != shp:
             raise ValueError("state_dict tensor %s has shape %s, expected %s" % (k, out[k].shape, shp))
     return out
+
+
+def _np(sd, k):
+    return sd[k].detach().to("cpu").float().numpy()
+
+
+def _bn(sd, prefix):
+    return np.stack([_np(sd, prefix + k) for k in _BN_KEYS])
+
+
+def pack_small(sd):
+    """the 12 small arrays of the C ABI (everything but the residual tower) from a DualNetwork state_dict"""
+    out = {
+        "conv_input_w": _np(sd, "conv_input.weight"), "bn_input": _bn(sd, "bn_input"),
+        "policy_conv_w": _np(sd, "policy_conv.weight").reshape(2, 128), "policy_bn": _bn(sd, "policy_bn"),
+        "policy_fc_w": _np(sd, "policy_fc.weight"), "policy_fc_b": _np(sd, "policy_fc.bias"),
+        "value_conv_w": _np(sd, "value_conv.weight").reshape(1, 128), "value_bn": _bn(sd, "value_bn"),
+        "value_fc1_w": _np(sd, "value_fc1.weight"), "value_fc1_b": _np(sd, "value_fc1.bias"),
+        "value_fc2_w": _np(sd, "value_fc2.weight"), "value_fc2_b": _np(sd, "value_fc2.bias"),
+    }
+    return _check_shapes(out, _SMALL_SHAPES)
+
+
+def pack_state_dict(sd):
+    """DualNetwork state_dict (dual_network.py:47-75; 216 entries) -> dict of the 14 contiguous fp32
+    arrays the C ABI takes (numpy, host)."""
+    n_blocks = 16
+    out = pack_small(sd)
+    out["res_conv_w"] = np.stack([np.stack([_np(sd, "residual_blocks.%d.conv1.weight" % i),
+                                            _np(sd, "residual_blocks.%d.conv2.weight" % i)]) for i in range(n_blocks)])
+    out["res_bn"] = np.stack([np.stack([_bn(sd, "residual_blocks.%d.bn1" % i), _bn(sd, "residual_blocks.%d.bn2" % i)])
+                              for i in range(n_blocks)])
+    return _check_shapes(out, {"res_conv_w": (16, 2, 128, 128, 3, 3), "res_bn": (16, 2, 4, 128)})
+
+
+def scattered_residual_tensors(sd):
+    """-> (32 conv tensors, 32 x 4 BatchNorm tensors) of the residual tower in layer order if every one of them is a
+    contiguous fp32 host tensor (the usual torch.load(..., map_location='cpu') result), else None"""
+    import torch
+    convs, bns = [], []
+    for i in range(16):
+        for j in (1, 2):
+            convs.append(sd["residual_blocks.%d.conv%d.weight" % (i, j)])
+            bns.append([sd["residual_blocks.%d.bn%d%s" % (i, j, k)] for k in _BN_KEYS])
+    for t, shp in [(c, (128, 128, 3, 3)) for c in convs] + [(b, (128,)) for row in bns for b in row]:
+        if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.device.type == "cpu" and t.is_contiguous()):
+            return None
+        if tuple(t.shape) != shp:
+            raise ValueError("state_dict tensor has shape %s, expected %s" % (tuple(t.shape), shp))
+    return convs, bns
 
 
 class History:
@@ -272,10 +308,25 @@ class Engine:
 
     # ---- weights
     def upload_state_dict(self, sd):
-        packed = pack_state_dict(sd)
-        w = UtttWeights(*[packed[k].ctypes.data for k in _WEIGHT_FIELDS])
-        _check(self.lib.uttt_upload_weights(self.h, C.byref(w), 0))
-        self._packed_keepalive = packed
+        """best.pth state_dict -> device (BN folded, tensor-core layouts).  Contiguous fp32 host tensors (pinned or not)
+        are copied from where they lie; anything else goes through one packed host copy first."""
+        res = scattered_residual_tensors(sd)
+        if res is None:
+            packed = pack_state_dict(sd)
+            w = UtttWeights(*[packed[k].ctypes.data for k in _WEIGHT_FIELDS])
+            _check(self.lib.uttt_upload_weights(self.h, C.byref(w), 0))
+            return
+        small = pack_small(sd)
+        w = UtttWeightsScattered()
+        for k in _WEIGHT_FIELDS:
+            if k in small:
+                setattr(w.small, k, small[k].ctypes.data)
+        convs, bns = res
+        for l in range(32):
+            w.res_conv_w[l] = convs[l].data_ptr()
+            for j in range(4):
+                w.res_bn[l][j] = bns[l][j].data_ptr()
+        _check(self.lib.uttt_upload_weights_scattered(self.h, C.byref(w), 0))      # synchronous: sd may go away after
 
     def upload_model(self, model):
         self.upload_state_dict(model.state_dict())
@@ -370,6 +421,10 @@ class Engine:
         out = np.zeros(64, np.int64)
         _check(self.lib.uttt_debug_batch_histogram(self.h, _ptr(out), 1 if reset else 0))
         return out
+
+    def set_profile_level(self, level):
+        """0: no per-kernel events during self-play, 1 (default): the trunk only, 2: tree / trunk / heads"""
+        _check(self.lib.uttt_set_profile_level(self.h, int(level)))
 
     def last_run_profile(self):
         """-> {kind: (ms, launches)} for tree / trunk / heads / all kernels of the last self-play run"""
