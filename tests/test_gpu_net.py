@@ -351,3 +351,26 @@ def test_state_dict_upload_paths_give_identical_networks(setup):
     bad["residual_blocks.3.conv2.weight"] = torch.zeros(128, 64, 3, 3)
     with pytest.raises(ValueError):
         e.upload_state_dict(bad)
+
+
+def test_profile_levels_and_identical_play(setup):
+    """uttt_set_profile_level only changes which kernels are bracketed by CUDA events: same games, same launch counts"""
+    import engine
+    e, model, sts = setup
+    e.upload_model(model)
+    hists = []
+    try:
+        for level, tree_timed, trunk_timed in ((0, False, False), (1, False, True), (2, True, True)):
+            e.set_profile_level(level)
+            st = e.selfplay_device(12, sims=20, batch=8, seed=3, evaluator=engine.EVAL_NET_BF16)
+            prof = e.last_run_profile()
+            assert (prof["tree"][0] > 0) == tree_timed and (prof["trunk"][0] > 0) == trunk_timed, (level, prof)
+            assert prof["trunk"][1] == st[3] and prof["all"][1] >= 2 * st[3]            # one trunk launch per round
+            h = e.selfplay_fetch(12)
+            hists.append((h.lens.copy(), h.actions.copy(), h.counts.copy()))
+        for other in hists[1:]:
+            assert all((a == b).all() for a, b in zip(hists[0], other))
+        with pytest.raises(RuntimeError):
+            e.set_profile_level(3)
+    finally:
+        e.set_profile_level(1)

@@ -49,8 +49,8 @@ def launches():
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, "%s_launches.md" % tag), "w") as f:
         f.write("# ncu launch list, round %s\n\n" % tag)
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 500 -c 1000 python tools/prof_selfplay.py --games 500`\n")
-        f.write("(C3 workload: 500 games, 50 sims/move, batch 8; launches 500..1499 of one self-play cycle; per-launch\n"
+        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 python tools/prof_selfplay.py --games 500`\n")
+        f.write("(C3 workload: 500 games, 50 sims/move, batch 8; launches 300..999 of one self-play cycle (two launches per round); per-launch\n"
                 "times are cold-cache and serialised -- compare SHARES, not absolutes)\n\n")
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -85,8 +85,10 @@ def full(name):
 
 
 launches()
-full("trunk1")     # trunk_tc_kernel     (one CTA per group; batch of 740 positions)
-full("trunk2")     # trunk_tc2_kernel<2> (CTA pair per group, 2 tiles per CTA; batch of 345 positions)
-full("trunk3")     # trunk_tc2_kernel<3> (CTA pair per group, 3 tiles per CTA; batch of 500 positions)
+full("trunk1")     # trunk_tc_kernel     (one CTA per group; batch of 740 positions; UTTT_TRUNK=1/2 only)
+full("trunk2")     # trunk_auto_kernel -> trunk_tc2_body<2> (CTA pair per group, 2 tiles per CTA; batch of 345 positions)
+full("trunk3")     # trunk_tc2_kernel<3> (CTA pair per group, 3 tiles per CTA; batch of 500 positions; UTTT_TRUNK=2 only)
+full("trunkpp")    # trunk_auto_kernel -> trunk_pp_body<1> (two groups in flight, cta_group::2; batch of 500 positions) + heads FC tail
+full("heads")      # heads_fc_kernel (standalone form of the heads' FC layers; 500 positions, warm L2)
 full("tree")
 full("rules")      # step / legal / encode / gather_planes / playout kernels at 2^22 (2^20) states (tools/prof_rules.py 22)
