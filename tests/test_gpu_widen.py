@@ -1,4 +1,6 @@
 """GPU: rows SURVEY 8(f) "next": the gating match and the vs-random evaluation on the engine."""
+import os
+
 import numpy as np
 import pytest
 
@@ -64,3 +66,48 @@ def test_evaluate_network_and_best_player_scripts(tmp_path, monkeypatch, capsys)
     ep.evaluate_best_player()
     out = capsys.readouterr().out
     assert "VS_Random" in out and 0.0 <= float(out.split("VS_Random")[1].split()[0]) <= 1.0
+
+
+def test_trainer_dropin_on_gpu(tmp_path, monkeypatch):
+    """train_network.py drop-in on the GPU: a self-play cycle's history goes into the trainer as device
+    tensors (no pickle), fp32 and bf16-autocast steps both reduce the loss, and the file protocol
+    (./data/*.history + ./model/best.pth -> ./model/latest.pth) works with the engine's own .history output."""
+    import copy
+    import pickle
+    import torch
+    import self_play_cpp
+    import train_network as tn
+    from dual_network import DualNetwork
+    torch.manual_seed(0)
+    model = DualNetwork().cuda().eval()
+    xs, ps, zs = self_play_cpp.history_tensors(model, n_games=6)
+    assert xs.is_cuda and xs.shape[1:] == (3, 9, 9) and ps.shape[1] == 81 and zs.shape[1] == 1 and xs.shape[0] >= 6 * 17
+    assert torch.allclose(ps.sum(1), torch.ones_like(ps[:, 0]), atol=1e-5)
+    ref = None
+    for bf16, graph in ((False, False), (False, True), (True, False), (True, True)):
+        m = copy.deepcopy(model)
+        torch.manual_seed(11)
+        losses = tn.train_tensors(m, xs, ps, zs, epochs=3, batch_size=64, bf16=bf16, graph=graph, log=lambda s: None)
+        assert len(losses) == 3 and np.isfinite(losses).all() and losses[-1] < losses[0], (bf16, graph, losses)
+        if not bf16:
+            # the CUDA-graph replay is the same training run as the eager loop (same batches, same updates; warm-up and
+            # capture leave no trace): losses agree to fp32 / cudnn-algorithm noise
+            if ref is None:
+                ref = losses
+            else:
+                assert np.allclose(losses, ref, rtol=2e-2), (losses, ref)
+    # file protocol
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("model"); os.makedirs("data")
+    torch.save(model.state_dict(), "model/best.pth")
+    hist = self_play_cpp._to_reference_format(xs.permute(0, 2, 3, 1).cpu().numpy(), ps.double().cpu().numpy(),
+                                              zs[:, 0].cpu().numpy().astype(np.int64))
+    with open("data/20260101000000.history", "wb") as f:
+        pickle.dump(hist, f)
+    monkeypatch.setattr(tn, "RN_EPOCHS", 1)
+    tn.train_network()
+    sd = torch.load("model/latest.pth", weights_only=True)
+    assert sd.keys() == model.state_dict().keys()
+    assert not torch.equal(sd["conv_input.weight"].cpu(), model.state_dict()["conv_input.weight"].cpu())
+    model2 = DualNetwork()
+    model2.load_state_dict(sd)                       # loadable by the engine / the next self-play cycle
