@@ -61,6 +61,7 @@ struct alignas(16) TreeCtl {
 
 struct TreeParams {
     int32_t n_trees, node_cap, sims, batch, mode, flags;
+    int32_t max_terminal;     // terminal descents one tree may retire per round (the rest continues next round)
     PackedState* root;        // [n_trees]
     PackedState* leaf_state;  // [n_trees]
     // throughput mode (tree_tp_kernels.cu): per tree up to TP_MAX_LEAVES pending leaves

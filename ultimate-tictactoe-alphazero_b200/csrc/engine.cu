@@ -258,6 +258,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     for (int i = 0; i < EV_POOL; i++) UTTT_CUDA_OK(cudaEventCreate(&e->ev[i]));
     t.policy = e->policy;
     t.value = e->value;
+    t.max_terminal = getenv("UTTT_MAX_TERMINAL") ? atoi(getenv("UTTT_MAX_TERMINAL")) : 4;   // measured on the 500-game cycle: 2..4 best, 8: +0.8 %, 50: +8 %
     t.dir_alpha = 0.3f;
     t.dir_eps = 0.25f;
     *out = e;

@@ -29,8 +29,6 @@
 
 namespace uttt {
 
-constexpr int MAX_TERMINAL_PER_ROUND = 8;
-
 // cpp/uttt_mcts.cpp:92-103: root expanded up-front with the uniform prior 1/L (never evaluated, Q-M1)
 __device__ void init_root(const TreeParams& P, const TreeView& T, TreeCtl& c, const PackedState& rs, int lane) {
     uint32_t lm[3];
@@ -281,7 +279,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
             if (lane == 0) atomicAdd(P.counters + 3, 1ull);
             // Every tree of the batch waits for the slowest warp of the round: bound the work of one round.  The
             // remaining simulations simply continue next round (same order, same results).
-            if (++n_terminal >= MAX_TERMINAL_PER_ROUND && c.sims_left > 0) { c.phase = PHASE_SEARCH; break; }
+            if (++n_terminal >= P.max_terminal && c.sims_left > 0) { c.phase = PHASE_SEARCH; break; }
             continue;
         }
 
