@@ -7,9 +7,9 @@
 //     -> C++ MCTS -> Python inference callback -> DualNetwork.forward
 // Here every game of a self-play cycle is a slot on the device; one "round" is
 //   tree_round kernel (apply previous evaluation, select next leaf, gather planes)
-//   -> evaluator (trunk + heads kernels, or the hash evaluator)
-// enqueued back to back on one stream with no host synchronisation except a progress check
-// every CHECK_EVERY rounds.
+//   -> evaluator (trunk_auto_kernel: tensor-core trunk + heads in one launch; or the fp32 kernels / hash evaluator)
+// enqueued back to back on one stream; the host keeps two windows of CHECK_EVERY rounds in flight and reads the
+// progress counters of a window while the next one runs.
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -146,10 +146,11 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         UTTT_CUDA_OK(launch_trunk_fp32(e->w, b.nn_planes, count, max_rows, b.act_a, b.act_b, s));
         e->prof_launches[1] += 1 + 2 * NET_BLOCKS;
     } else if (evaluator == UTTT_EVAL_NET_BF16) {
-        // conv_input runs inside the trunk kernels (tensor pipe, "layer -1").  Two trunk variants are enqueued; each
-        // reads the queue length on the device and exits at once if the batch is not in its range: small batches
-        // (one wave of CTA pairs) are latency-bound -> cluster variant, larger ones are throughput-bound -> one CTA
-        // per group with 4 accumulator tiles.  Counted as ONE trunk launch per round.
+        // conv_input runs inside the trunk kernels (tensor pipe, "layer -1").  The queue length is only known on the
+        // device: small batches (one wave of CTA pairs) are latency-bound -> one group per pair with the next layer
+        // overlapping the epilogue, larger ones are throughput-bound -> two groups in flight with cta_group::2 MMAs.
+        // Variant 4 makes that choice inside one launch; the older variants enqueue one kernel per range and the ones
+        // that do not match exit at once.  Counted as ONE trunk launch per round.
         if (ev3) cudaEventRecord(ev3[0], s);
         if (e->trunk_variant == 4) {
             // one launch: the kernel branches on the queue length (net_auto.cu); batches above 7 positions per CTA pair
