@@ -117,7 +117,7 @@ struct NetWeights {
     float* res_b;         // [32][128]
     // bf16 tensor-core path: [layer][72 K-blocks, tcx::kblock_of][2 k-panels][cout 128][8]  (UMMA canonical K-major, no swizzle)
     __nv_bfloat16* res_w_bf16;
-    __nv_bfloat16* conv_in_w_bf16;   // conv_input as a K=16-per-tap tensor-core layer: [12 taps (9 used)][2][128][8]
+    __nv_bfloat16* conv_in_w_bf16;   // conv_input as a K=16-per-tap tensor-core layer: [16 tap slots (9 used)][2][128][8]
     float* bias_all;                 // [33][128]: conv_input shift followed by the 32 trunk layers' shifts
     __nv_bfloat16* bias_blk;         // [33][2][128][8] bf16: each layer's shift as a tensor-core B block (hi, lo in k = 0, 1)
     // the same three arrays for cta_group::2 MMAs (net_pp.cu): the B operand is split by output channel between the two

@@ -383,9 +383,9 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
     for (int j = 0; j < 256; j++)
         for (int i = 0; i < 81; i++) v1_t[i * 256 + j] = v1w[j * 81 + i];
 
-    // conv_input for the tensor pipe: [12 tap slots (9 used)][2 panels][128 co][8 ci]; channels 3..15 are zero
+    // conv_input for the tensor pipe: [16 tap slots (9 used)][2 panels][128 co][8 ci]; channels 3..15 are zero
     {
-        std::vector<__nv_bfloat16> ci_h((size_t)12 * 2 * 128 * 8, __float2bfloat16(0.0f));
+        std::vector<__nv_bfloat16> ci_h((size_t)16 * 2 * 128 * 8, __float2bfloat16(0.0f));     // 16 tap slots, 9 used
         for (int tap = 0; tap < 9; tap++)
             for (int ci = 0; ci < 3; ci++)
                 for (int co = 0; co < 128; co++)
@@ -803,6 +803,10 @@ int uttt_debug_trunk_timeline(uttt_engine* e, int64_t* out128) {
         fprintf(stderr, "pp detail layer 20 (rel): A: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld | B: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld\n",
                 0ll, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - d[0], d[8] - d[0], d[9] - d[0], d[10] - d[0], d[11] - d[0],
                 d[12] - d[0], d[13] - d[0], d[14] - d[0]);
+        long long au[3];
+        UTTT_CUDA_OK(cudaMemcpy(au, e->tc_dbg + 200, sizeof(au), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "trunk_auto_kernel CTA 0 (cycles rel. entry): body done %lld, heads FC done %lld (warp 0's exit; heads = %lld)\n",
+                au[1] - au[0], au[2] - au[0], au[2] - au[1]);
         fprintf(stderr, "trunk phases (cycles rel. entry): setup %lld, first MMA %lld, last epilogue %lld, exit %lld\n", ph[1] - ph[0],
                 (long long)out128[0] - ph[0], ph[2] - ph[0], ph[3] - ph[0]);
     }

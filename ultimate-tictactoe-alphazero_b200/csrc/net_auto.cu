@@ -24,12 +24,15 @@ trunk_auto_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __r
                   const int32_t* __restrict__ count, int small_cap, int max_count, long long* dbg,
                   HeadsFC fc, float* policy, float* value /* null: the heads' FC layers are a separate kernel */) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    const bool stamp = dbg && blockIdx.x == 0 && threadIdx.x == 0;          // diagnostics: phases of CTA 0
+    if (stamp) dbg[200] = clock64();
     const int n_pos = *count;
     const bool small = n_pos <= small_cap;
     if (small)
         tc2::trunk_tc2_body<2>(wq, wq_in, wq_bias, planes, headw, headfeat, skip, count, 0, small_cap, dbg);
     else
         pp::trunk_pp_body<1>(wq2, wq2_in, wq2_bias, planes, headw, headfeat, skip, count, small_cap, max_count, dbg);
+    if (stamp) dbg[201] = clock64();
     if (policy == nullptr || n_pos > max_count) return;
     // Fused heads (the host passes policy / value only if no batch can exceed one group per pair): the pair's head
     // features were written to global memory by both CTAs' last epilogues and ordered by the cluster barrier that ends
@@ -43,6 +46,7 @@ trunk_auto_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __r
     static_assert((pp::Cfg<1>::MAX_PA + pp::Cfg<1>::MAX_PB + 1) / 2 <= HEADS_P, "one heads call per CTA");
     if (np == 0) return;
     heads_fc_block(fc, headfeat, row0, 2, np, policy, value, 1, reinterpret_cast<float*>(smem));
+    if (stamp) dbg[202] = clock64();
 }
 
 cudaError_t trunk_auto_init() {

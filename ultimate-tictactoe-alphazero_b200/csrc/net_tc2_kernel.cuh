@@ -30,16 +30,20 @@ namespace tc2 {
 
 constexpr int POS_ROWS = 100;
 constexpr int LEAD = 11;
-constexpr int STAGE_BYTES = 16384;
-constexpr int STAGES_PER_LAYER = 18;
-constexpr int IN_STAGES = 3;                    // conv_input: 9 taps x (K=16: 3 real channels) in 3 stages of 4 taps
+constexpr int STAGE_BLOCKS = 8;                 // K-blocks (MMAs per tile) per weight stage.  An issuer thread pays one
+                                                // barrier wait and one commit per stage (200+ cycles each while the tensor
+                                                // pipe saturates shared memory): with 4-block stages a CTA that owns ONE tile
+                                                // (batches of up to 148 positions) was issue-bound at ~93 cycles per MMA
+constexpr int STAGE_BYTES = STAGE_BLOCKS * 4096;
+constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
+constexpr int IN_STAGES = 2;                    // conv_input: 9 taps x (K=16: 3 real channels) in 16 tap slots
 constexpr int BIAS_BYTES = 4096;                // one [2 panels][128 co][8] block: BN shift as bf16 hi + lo in k = 0, 1
 constexpr int GROUP_STAGES = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);   // every layer starts with its bias block
 constexpr int GROUP_LAYERS = NET_LAYERS + 1;     // conv_input runs as layer -1 through the same pipeline
 constexpr uint32_t IDESC = tcx::IDESC_M128_N128_BF16;
 
-// LT = accumulator tiles per CTA.  LT=2: up to 5 positions per CTA pair (2+2 tiles), 8 weight stages.
-//                                   LT=3: up to 7 positions per CTA pair (3+3 tiles), 6 weight stages.
+// LT = accumulator tiles per CTA.  LT=2: up to 5 positions per CTA pair (2+2 tiles), 4 weight stages of 32 KiB.
+//                                   LT=3: up to 7 positions per CTA pair (3+3 tiles), 3 weight stages.
 template <int LT>
 struct Cfg {
     static constexpr int LOC_TILES = LT;
@@ -47,7 +51,7 @@ struct Cfg {
     static constexpr int AROWS = (LEAD + 128 * LT + 11 + 7) / 8 * 8;
     static constexpr int PANEL_BYTES = AROWS * 16;
     static constexpr int A_BYTES = 18 * PANEL_BYTES;      // 16 channel panels + the constant panel pair of the bias MMA
-    static constexpr int STAGES = (LT == 2) ? 8 : 6;
+    static constexpr int STAGES = (LT == 2) ? 4 : 3;
     // LT = 2 has TMEM for two accumulators per tile (4 x 128 = 512 columns): the layers alternate between them, and the
     // epilogue publishes its output per 16-column chunk (NQ act_ready barriers per tile), so the MMAs of layer L+1
     // run while the epilogue of layer L is still converting the other chunks.  (LT = 3 has one spare accumulator only;
@@ -80,7 +84,7 @@ __host__ __device__ inline int group_positions(int n_pos, int n_pairs) {
 // pp::trunk_pp_body); the __global__ wrappers are in net_tc2.cu
 template <int LT>
 __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2][128][8] bf16
-                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [12 taps (9 used)][2][128][8] bf16
+                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [16 tap slots (9 used)][2][128][8] bf16
                  const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
                  const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
                  const float* __restrict__ headw,        // [3][128] policy conv (2) + value conv, BN scale folded; [384..386] shifts
@@ -388,14 +392,14 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                 }
                 advance();
                 if (layer < 0) {
-                    // conv_input: block j of stage s is tap 4s+j, K = 16 (channel panels 0,1)
+                    // conv_input: block j of stage s is tap 8s+j, K = 16 (channel panels 0,1)
 #pragma unroll
                     for (int s = 0; s < IN_STAGES; s++) {
                         next_stage();
                         if (leader) {
 #pragma unroll
-                            for (int j = 0; j < 4; j++) {
-                                const int tap = 4 * s + j;
+                            for (int j = 0; j < STAGE_BLOCKS; j++) {
+                                const int tap = STAGE_BLOCKS * s + j;
                                 if (tap < 9)
                                     umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)((tap / 3 - 1) * 10 + (tap % 3 - 1)),
                                               b_st + (uint64_t)(j * 256), IDESC, 1u);
@@ -409,14 +413,14 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                         advance();
                     }
                 } else {
-                    // stage s holds K-blocks 4s .. 4s+3 in the order of tcx::kblock_of (channel-quarter-major); the first
+                    // stage s holds K-blocks 8s .. 8s+7 in the order of tcx::kblock_of (channel-quarter-major); the first
                     // block of quarter q waits for the epilogue's q-th chunk of the previous layer
 #pragma unroll
                     for (int s = 0; s < STAGES_PER_LAYER; s++) {
                         next_stage();
 #pragma unroll
-                        for (int ks = 0; ks < 4; ks++) {
-                            const int m = 4 * s + ks, q = m / 18, r = m % 18, tap = r >> 1, unit = q + 4 * (r & 1);
+                        for (int ks = 0; ks < STAGE_BLOCKS; ks++) {
+                            const int m = STAGE_BLOCKS * s + ks, q = m / 18, r = m % 18, tap = r >> 1, unit = q + 4 * (r & 1);
                             if (r == 0 && C::two_accumulators(lt)) {
                                 wait_act(q, apar);
                                 if (q == 0 && dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[layer * 4 + 0] = clock64();
