@@ -124,7 +124,8 @@ int uttt_upload_weights(uttt_engine *e, const uttt_weights *w, int on_device);
  * residual convolutions `residual_blocks.{b}.conv{1,2}.weight` (index 2*b + j, each (128,128,3,3)) and their
  * BatchNorm vectors `residual_blocks.{b}.bn{1,2}.{weight,bias,running_mean,running_var}` (128 each) are read from
  * the caller's 160 tensors where they lie (pinned host memory -> one DMA each, no host-side concatenation);
- * `small` holds the remaining 12 arrays as in uttt_weights (its res_conv_w / res_bn are ignored).              */
+ * `small` holds the remaining 12 arrays as in uttt_weights (its res_conv_w / res_bn are ignored); `on_device` describes
+ * `small` only: each of the 160 tensors may lie in host or device memory (copied with cudaMemcpyDefault).            */
 typedef struct {
     uttt_weights small;
     const float *res_conv_w[32];

@@ -339,9 +339,11 @@ def test_state_dict_upload_paths_give_identical_networks(setup):
     q0, w0 = _forward(e, sts[:64], engine.EVAL_NET_FP32)
     pinned = {k: v.pin_memory() for k, v in sd.items()}
     halves = {k: v.double() for k, v in sd.items()}                  # wrong dtype -> packed path (converted to fp32)
-    on_gpu = {k: v.cuda() for k, v in sd.items()}                    # device tensors -> packed path
-    assert engine.scattered_residual_tensors(halves) is None and engine.scattered_residual_tensors(on_gpu) is None
-    for other in (pinned, halves, on_gpu):
+    on_gpu = {k: v.cuda() for k, v in sd.items()}                    # device tensors: read where they lie, too
+    strided = {k: (torch.stack([v, v], -1)[..., 0] if v.dim() == 4 else v) for k, v in sd.items()}   # non-contiguous -> packed
+    assert engine.scattered_residual_tensors(halves) is None and engine.scattered_residual_tensors(strided) is None
+    assert engine.scattered_residual_tensors(on_gpu) is not None
+    for other in (pinned, halves, on_gpu, strided):
         e.upload_state_dict({k: torch.zeros_like(v) for k, v in sd.items()})       # really replaced in between
         e.upload_state_dict(other)
         p, v = _forward(e, sts[:300], engine.EVAL_NET_BF16)

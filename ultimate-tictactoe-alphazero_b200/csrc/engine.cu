@@ -346,10 +346,12 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
         const size_t per = (size_t)128 * 128 * 9;
         for (int l = 0; l < 32; l++) {
             UTTT_CHECK(res_tab[l] != nullptr, "null weight tensor");
-            UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res + l * per, res_tab[l], per * sizeof(float), kind, e->stream));
+            // (cudaMemcpyDefault: each tensor may lie in host or device memory, whatever `on_device` says about `small`)
+            UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res + l * per, res_tab[l], per * sizeof(float), cudaMemcpyDefault, e->stream));
             for (int j = 0; j < 4; j++) {
                 UTTT_CHECK(res_bn_tab[l][j] != nullptr, "null weight tensor");
-                UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res_bn + (l * 4 + j) * 128, res_bn_tab[l][j], 128 * sizeof(float), kind, e->stream));
+                UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res_bn + (l * 4 + j) * 128, res_bn_tab[l][j], 128 * sizeof(float), cudaMemcpyDefault,
+                                             e->stream));
             }
         }
     } else {
@@ -803,8 +805,11 @@ int uttt_debug_trunk_timeline(uttt_engine* e, int64_t* out128) {
         fprintf(stderr, "pp detail layer 20 (rel): A: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld | B: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld\n",
                 0ll, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - d[0], d[8] - d[0], d[9] - d[0], d[10] - d[0], d[11] - d[0],
                 d[12] - d[0], d[13] - d[0], d[14] - d[0]);
-        long long au[3];
+        long long au[10];
         UTTT_CUDA_OK(cudaMemcpy(au, e->tc_dbg + 200, sizeof(au), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "heads FC tail (cycles rel. body done): barriers ready %lld, features loaded %lld, chunk 0/1/2 landed %lld %lld %lld, "
+                "policy FC done %lld, all FC done %lld, exit %lld\n", au[3] - au[1], au[4] - au[1], au[5] - au[1], au[6] - au[1],
+                au[7] - au[1], au[8] - au[1], au[9] - au[1], au[2] - au[1]);
         fprintf(stderr, "trunk_auto_kernel CTA 0 (cycles rel. entry): body done %lld, heads FC done %lld (warp 0's exit; heads = %lld)\n",
                 au[1] - au[0], au[2] - au[0], au[2] - au[1]);
         fprintf(stderr, "trunk phases (cycles rel. entry): setup %lld, first MMA %lld, last epilogue %lld, exit %lld\n", ph[1] - ph[0],

@@ -45,7 +45,7 @@ trunk_auto_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __r
     const int np = row0 < last ? (last - row0 + 1) >> 1 : 0;
     static_assert((pp::Cfg<1>::MAX_PA + pp::Cfg<1>::MAX_PB + 1) / 2 <= HEADS_P, "one heads call per CTA");
     if (np == 0) return;
-    heads_fc_block(fc, headfeat, row0, 2, np, policy, value, 1, reinterpret_cast<float*>(smem));
+    heads_fc_block(fc, headfeat, row0, 2, np, policy, value, 1, reinterpret_cast<float*>(smem), stamp ? dbg + 203 : nullptr);
     if (stamp) dbg[202] = clock64();
 }
 

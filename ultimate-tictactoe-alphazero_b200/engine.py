@@ -221,7 +221,7 @@ def pack_state_dict(sd):
 
 def scattered_residual_tensors(sd):
     """-> (32 conv tensors, 32 x 4 BatchNorm tensors) of the residual tower in layer order if every one of them is a
-    contiguous fp32 host tensor (the usual torch.load(..., map_location='cpu') result), else None"""
+    contiguous fp32 tensor in host or CUDA memory (what torch.load(..., map_location=...) gives), else None"""
     import torch
     convs, bns = [], []
     for i in range(16):
@@ -229,7 +229,7 @@ def scattered_residual_tensors(sd):
             convs.append(sd["residual_blocks.%d.conv%d.weight" % (i, j)])
             bns.append([sd["residual_blocks.%d.bn%d%s" % (i, j, k)] for k in _BN_KEYS])
     for t, shp in [(c, (128, 128, 3, 3)) for c in convs] + [(b, (128,)) for row in bns for b in row]:
-        if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.device.type == "cpu" and t.is_contiguous()):
+        if not (isinstance(t, torch.Tensor) and t.dtype == torch.float32 and t.device.type in ("cpu", "cuda") and t.is_contiguous()):
             return None
         if tuple(t.shape) != shp:
             raise ValueError("state_dict tensor has shape %s, expected %s" % (tuple(t.shape), shp))
@@ -308,8 +308,8 @@ class Engine:
 
     # ---- weights
     def upload_state_dict(self, sd):
-        """best.pth state_dict -> device (BN folded, tensor-core layouts).  Contiguous fp32 host tensors (pinned or not)
-        are copied from where they lie; anything else goes through one packed host copy first."""
+        """best.pth state_dict -> device (BN folded, tensor-core layouts).  Contiguous fp32 tensors (host, pinned or not, or
+        CUDA memory) are copied from where they lie; anything else goes through one packed host copy first."""
         res = scattered_residual_tensors(sd)
         if res is None:
             packed = pack_state_dict(sd)
