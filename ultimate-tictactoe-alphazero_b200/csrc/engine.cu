@@ -24,7 +24,7 @@ using namespace uttt;
 
 namespace {
 
-constexpr int CHECK_EVERY = 16;
+constexpr int CHECK_EVERY = 8;             // rounds per host progress check (self-play: per window)
 constexpr int N_LANES = 2;
 constexpr int N_WINDOWS = 2;           // self-play keeps two windows of CHECK_EVERY rounds in flight
 constexpr int EV_POOL = N_WINDOWS * CHECK_EVERY * 4 * N_LANES;

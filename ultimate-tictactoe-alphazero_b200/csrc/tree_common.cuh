@@ -27,12 +27,19 @@ __device__ __forceinline__ int node_vloss(const uint4& q) { return (int)(q.x >> 
 __device__ __forceinline__ uint32_t node_base(const uint4& q) { return q.w & 0xFFFFFu; }
 __device__ __forceinline__ int node_cnt(const uint4& q) { return (int)(q.w >> 20); }
 
-__device__ __forceinline__ PackedState warp_load_state(const PackedState* p, int lane) {
-    uint32_t x = (lane < 8) ? reinterpret_cast<const uint32_t*>(p)[lane] : 0u;
+// a packed state is loaded by lanes 0..7 (one word each) and handed round by shuffles; the two halves are separate so
+// that a kernel can issue several such loads before it consumes the first (one L2 round trip instead of one each)
+__device__ __forceinline__ uint32_t warp_load_state_issue(const PackedState* p, int lane) {
+    return (lane < 8) ? reinterpret_cast<const uint32_t*>(p)[lane] : 0u;
+}
+__device__ __forceinline__ PackedState warp_load_state_finish(uint32_t x) {
     PackedState s;
 #pragma unroll
     for (int i = 0; i < 8; i++) s.w[i] = __shfl_sync(FULL, x, i);
     return s;
+}
+__device__ __forceinline__ PackedState warp_load_state(const PackedState* p, int lane) {
+    return warp_load_state_finish(warp_load_state_issue(p, lane));
 }
 __device__ __forceinline__ void warp_store_state(PackedState* p, const PackedState& s, int lane) {
     uint32_t x = s.w[0];

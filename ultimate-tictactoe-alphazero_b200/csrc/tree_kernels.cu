@@ -65,8 +65,7 @@ __device__ void backup(const TreeView& T, int plen, int k, const float* vals, in
 }
 
 // cpp/uttt_mcts.cpp:138-167 for the k queued copies of one leaf
-__device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, int t, int lane) {
-    PackedState st = warp_load_state(P.leaf_state + t, lane);
+__device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, const PackedState& st, int lane) {
     uint32_t lm[3];
     int L = legal_mask(st, lm);
     int k = c.pend_k, plen = c.path_len;
@@ -155,17 +154,20 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
     // the other parity's counter was consumed by the previous round's evaluator: reset it
     if (blockIdx.x == 0 && threadIdx.x == 0) P.nn_count[P.parity ^ 1] = 0;
     if (t >= P.n_trees) return;
+    // the control block, the pending leaf and the root position have nothing to wait for: one L2 round trip for the three
+    const uint32_t leaf_raw = warp_load_state_issue(P.leaf_state + t, lane);
+    const uint32_t root_raw = warp_load_state_issue(P.root + t, lane);
     TreeCtl c = P.ctl[t];
     if (c.phase == PHASE_DONE) return;
     TreeView T = view_of(P, t);
 
     if (c.phase == PHASE_PENDING) {
-        apply_leaf(P, T, c, t, lane);
+        apply_leaf(P, T, c, warp_load_state_finish(leaf_raw), lane);
         if (c.phase == PHASE_DONE) { if (lane == 0) P.ctl[t] = c; return; }
         c.phase = PHASE_SEARCH;
     }
 
-    PackedState root = warp_load_state(P.root + t, lane);
+    PackedState root = warp_load_state_finish(root_raw);
     int n_terminal = 0;
     for (;;) {
         if (c.sims_left <= 0) {
