@@ -95,6 +95,8 @@ struct TreeParams {
     uint8_t* hist_actions;         // [n_games][81]
     int32_t* hist_len;             // [n_games]
     int8_t* hist_final;            // [n_games]
+    unsigned long long* dbg_tree;  // diagnostics (null = off): [16 classes][3] = sum of cycles, warps, max cycles per class of
+                                   // a tree's round: class = min(terminal descents, 7) + 8 * (a move was decided)
 };
 
 // kernels' host launchers (each returns cudaGetLastError of the launch)

@@ -259,6 +259,11 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     for (int i = 0; i < EV_POOL; i++) UTTT_CUDA_OK(cudaEventCreate(&e->ev[i]));
     t.policy = e->policy;
     t.value = e->value;
+    t.dbg_tree = nullptr;
+    if (getenv("UTTT_DEBUG_TREE")) {
+        if (ealloc(e, &t.dbg_tree, 48)) { uttt_destroy(e); return 1; }
+        UTTT_CUDA_OK(cudaMemset(t.dbg_tree, 0, 48 * sizeof(unsigned long long)));
+    }
     t.max_terminal = getenv("UTTT_MAX_TERMINAL") ? atoi(getenv("UTTT_MAX_TERMINAL")) : 4;   // measured on the 500-game cycle: 2..4 best, 8: +0.8 %, 50: +8 %
     t.dir_alpha = 0.3f;
     t.dir_eps = 0.25f;
@@ -757,6 +762,15 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
         }
     }
     UTTT_CUDA_OK(cudaMemcpy(e->h_counters, t.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (t.dbg_tree) {              // UTTT_DEBUG_TREE: cycles of one tree's round by class (terminal descents, move decided)
+        unsigned long long d[48];
+        UTTT_CUDA_OK(cudaMemcpy(d, t.dbg_tree, sizeof(d), cudaMemcpyDeviceToHost));
+        UTTT_CUDA_OK(cudaMemset(t.dbg_tree, 0, sizeof(d)));
+        for (int c = 0; c < 16; c++)
+            if (d[3 * c + 1])
+                fprintf(stderr, "tree round class terminal=%d moved=%d: %llu warps, mean %llu cycles, max %llu\n", c & 7, c >> 3,
+                        d[3 * c + 1], d[3 * c] / d[3 * c + 1], d[3 * c + 2]);
+    }
     UTTT_CHECK(done, "self-play did not finish within %lld rounds", (long long)max_rounds);
     e->prof_launches[3] = e->prof_launches[0] + e->prof_launches[1] + e->prof_launches[2];
     if (stats) {

@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
     // the other parity's counter was consumed by the previous round's evaluator: reset it
     if (blockIdx.x == 0 && threadIdx.x == 0) P.nn_count[P.parity ^ 1] = 0;
     if (t >= P.n_trees) return;
+    const long long t_start = P.dbg_tree ? clock64() : 0;
+    int dbg_moved = 0;
     // the control block, the pending leaf and the root position have nothing to wait for: one L2 round trip for the three
     const uint32_t leaf_raw = warp_load_state_issue(P.leaf_state + t, lane);
     const uint32_t root_raw = warp_load_state_issue(P.root + t, lane);
@@ -184,6 +186,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
             warp_store_state(P.hist_states + hrow, root, lane);
             for (int a = lane; a < 81; a += 32)
                 P.hist_counts[hrow * 81 + a] = legal_bit(lm, a) ? (uint16_t)node_n(T.node[1 + legal_rank(lm, a)]) : (uint16_t)0;
+            dbg_moved = 8;
             int action = sample_move(P, T, c, lm, lane);
             if (lane == 0) P.hist_actions[hrow] = (uint8_t)action;
             PackedState nx;
@@ -304,6 +307,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
         break;
     }
     if (lane == 0) P.ctl[t] = c;
+    if (P.dbg_tree && lane == 0) {
+        unsigned long long dt = (unsigned long long)(clock64() - t_start);
+        unsigned long long* d = P.dbg_tree + 3 * (min(n_terminal, 7) + dbg_moved);
+        atomicAdd(d, dt); atomicAdd(d + 1, 1ull); atomicMax(d + 2, dt);
+    }
 }
 
 // Deterministic integer-hash evaluator on the device (the "oracle evaluator" of the parity tests):
