@@ -247,10 +247,13 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
             uint32_t bestx = 0u, bestlink = 0u;
             auto consider = [&](const uint4& q, int i) {
                 int n = node_n(q);
-                float w = __uint_as_float(q.y), p = __uint_as_float(q.z);
-                float qv = (n > 0) ? __fdiv_rn(-w, (float)n) : 0.0f;
-                float u = __fdiv_rn(__fmul_rn(p, sq), (float)(1 + n));
-                float s = __fadd_rn(qv, u);
+                // unvisited child (most of a k-fold duplicated list): q = 0 and u = (p*sq)/1, so pucb = p*sq exactly --
+                // the two IEEE divisions are only executed for visited children
+                float s = __fmul_rn(__uint_as_float(q.z), sq);
+                if (n > 0) {
+                    float qv = __fdiv_rn(-__uint_as_float(q.y), (float)n);
+                    s = __fadd_rn(qv, __fdiv_rn(s, (float)(1 + n)));
+                }
                 if (s > best) { best = s; besti = i; bestx = q.x; bestlink = q.w; }
             };
             if (lane < cnt) consider(c0, lane);
