@@ -53,9 +53,16 @@ __device__ void backup(const TreeView& T, int plen, int k, const float* vals, in
         uint2* nw = reinterpret_cast<uint2*>(T.node + node);     // {n|action, w}
         uint2 q = *nw;
         float w = __uint_as_float(q.y);
-        for (int c = 0; c < k; c++) {
-            float v = vals ? vals[(size_t)c * vstride] : v_single;
-            w = __fadd_rn(w, flip ? -v : v);
+        if (vals && vstride != 0) {
+            for (int c = 0; c < k; c++) {
+                float v = vals[(size_t)c * vstride];
+                w = __fadd_rn(w, flip ? -v : v);
+            }
+        } else {
+            // k identical values: still k sequential fp32 adds (w += v k times != w += k*v), but one load
+            float v = vals ? vals[0] : v_single;
+            v = flip ? -v : v;
+            for (int c = 0; c < k; c++) w = __fadd_rn(w, v);
         }
         q.y = __float_as_uint(w);
         q.x += (uint32_t)k;                                       // n lives in the low 16 bits
@@ -89,8 +96,8 @@ __device__ void apply_leaf(const TreeParams& P, const TreeView& T, TreeCtl& c, c
             while (m) {
                 int a = 27 * j + __ffs((int)m) - 1;
                 m &= m - 1u;
-                float v0 = __shfl_sync(FULL, p0, a & 31), v1 = __shfl_sync(FULL, p1, a & 31), v2 = __shfl_sync(FULL, p2, a & 31);
-                sum = __fadd_rn(sum, a < 32 ? v0 : (a < 64 ? v1 : v2));
+                const float src = a < 32 ? p0 : (a < 64 ? p1 : p2);          // `a` is warp-uniform: one shuffle per addend
+                sum = __fadd_rn(sum, __shfl_sync(FULL, src, a & 31));
             }
         }
         float uni = (L > 0) ? __fdiv_rn(1.0f, (float)L) : 0.0f;
