@@ -376,3 +376,25 @@ def test_profile_levels_and_identical_play(setup):
             e.set_profile_level(3)
     finally:
         e.set_profile_level(1)
+
+
+def test_network_selfplay_is_reproducible_run_to_run(setup):
+    """Slot mode (net_auto.cu): with up to 518 concurrent games the leaves of a round are ordered by slot, not by their
+    arrival at an atomic counter, and the first games go to the slots in slot order -- so which leaves fall into the
+    split-K group of the large-batch trunk, and therefore every bit of the run, is a function of the seed alone.
+    420 games keep the batches in the 371..518 band where that group exists."""
+    import engine
+    e, model, sts = setup
+    eng = engine.Engine(n_slots=420, max_sims=16, max_batch=8, max_games=420)
+    try:
+        eng.upload_model(model)
+        runs = []
+        for _ in range(3):
+            h = eng.selfplay(420, sims=16, batch=8, seed=5, evaluator=engine.EVAL_NET_BF16)
+            runs.append((h.lens.copy(), h.actions.copy(), h.counts.copy()))
+        hist = eng.batch_histogram()
+        assert hist[24:33].sum() > 0, hist             # launches with 384..527 positions did occur
+        for other in runs[1:]:
+            assert all((a == b).all() for a, b in zip(runs[0], other))
+    finally:
+        eng.close()

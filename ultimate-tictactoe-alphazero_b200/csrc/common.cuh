@@ -61,6 +61,7 @@ struct alignas(16) TreeCtl {
 
 struct TreeParams {
     int32_t n_trees, node_cap, sims, batch, mode, flags;
+    int32_t slot0;            // global index of this lane's first slot (self-play: slot s starts with game game0 + s)
     int32_t max_terminal;     // terminal descents one tree may retire per round (the rest continues next round)
     PackedState* root;        // [n_trees]
     PackedState* leaf_state;  // [n_trees]
@@ -95,6 +96,8 @@ struct TreeParams {
     uint8_t* hist_actions;         // [n_games][81]
     int32_t* hist_len;             // [n_games]
     int8_t* hist_final;            // [n_games]
+    uint8_t* slot_flags;           // slot mode (null = off): a leaf stays in row t of the evaluator buffers, slot_flags[t] = the
+                                   // tree queued one this round (trunk_auto_kernel counts and orders them: reproducible runs)
     unsigned long long* dbg_tree;  // diagnostics (null = off): [16 classes][3] = sum of cycles, warps, max cycles per class of
                                    // a tree's round: class = min(terminal descents, 7) + 8 * (a move was decided)
 };
@@ -169,7 +172,8 @@ cudaError_t launch_trunk_pp_large(const NetWeights& w, const __nv_bfloat16* plan
 // one launch for every batch up to trunk_pp_cap1: device-side choice between trunk_tc2_kernel<2> and trunk_pp_kernel<1>
 // (policy / value non-null: the heads' FC layers run in the kernel's tail; requires max_rows <= trunk_pp_cap1)
 cudaError_t launch_trunk_auto(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count, int max_rows,
-                              float* skip, int n_sm, cudaStream_t s, long long* dbg, float* policy, float* value);
+                              float* skip, int n_sm, cudaStream_t s, long long* dbg, float* policy, float* value,
+                              const uint8_t* slot_flags = nullptr, int n_slots = 0);
 cudaError_t trunk_auto_init();
 int trunk_tc2_capacity(int n_sm);    // largest batch the cluster variant evaluates in one wave
 int trunk_tc_smem_bytes();

@@ -77,6 +77,7 @@ struct uttt_engine {
     float* headfeat;        // [rows][243] head 1x1-conv outputs written by the tensor-core trunk
     float* tc_resid;        // [n_sm][32][512][4] fp32 residual stream of the tensor-core trunk (per CTA)
     int32_t* fwd_count;     // device int for uttt_net_forward
+    uint8_t* slot_flags;    // [n_slots] slot mode of the evaluator queue (see net_auto.cu)
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0, then [64] histogram of batch sizes (diagnostics)
     int prof_level;         // self-play kernel timing: 2 = tree / trunk / heads events every round, 1 = trunk only, 0 = none
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
@@ -113,6 +114,8 @@ struct EvalBufs {
     const int32_t* nn_k;
     const __nv_bfloat16* nn_planes;
     float *policy, *value, *act_a, *act_b, *resid, *headfeat;
+    const uint8_t* slot_flags;     // non-null: slot mode (the tree kernel left the leaves in their trees' rows)
+    int n_slots;
 };
 
 EvalBufs bufs_of(uttt_engine* e, size_t first_slot, int lane) {
@@ -127,6 +130,8 @@ EvalBufs bufs_of(uttt_engine* e, size_t first_slot, int lane) {
     b.act_b = e->act_b + first_row * 81 * 128;
     b.headfeat = e->headfeat + first_row * 243;
     b.resid = e->tc_resid + (size_t)lane * e->n_sm * 512 * 64;     // fp16 panels: 128 KiB per CTA
+    b.slot_flags = nullptr;
+    b.n_slots = 0;
     return b;
 }
 
@@ -157,8 +162,10 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
             // (only possible when max_rows allows them) are left to the 10-positions-per-pair instantiation
             // (if no batch can exceed one group per pair, the heads' FC layers run in the tail of the same kernel)
             heads_fused = max_rows <= trunk_pp_cap1(e->n_sm);
+            UTTT_CHECK(heads_fused || !b.slot_flags, "slot mode needs the fused heads");
             UTTT_CUDA_OK(launch_trunk_auto(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
-                                           heads_fused ? b.policy : nullptr, heads_fused ? b.value : nullptr));
+                                           heads_fused ? b.policy : nullptr, heads_fused ? b.value : nullptr, b.slot_flags,
+                                           b.n_slots));
             if (!heads_fused)
                 UTTT_CUDA_OK(launch_trunk_pp_large(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
         } else if (e->trunk_variant == 3) {
@@ -192,6 +199,14 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
     e->prof_launches[2] += 1;
     if (ev3 && e->prof_level >= 2) cudaEventRecord(ev3[2], s);
     return 0;
+}
+
+// Slot mode (net_auto.cu: reproducible runs with the split-K group of the large-batch trunk): the reference-exact search
+// with the tensor-core evaluator, when one trunk_auto_kernel launch with fused heads covers every possible batch.
+bool slot_mode_applies(uttt_engine* e, int evaluator, bool throughput, int rows) {
+    static const bool enabled = !(getenv("UTTT_SLOT_MODE") && atoi(getenv("UTTT_SLOT_MODE")) == 0);
+    return enabled && evaluator == UTTT_EVAL_NET_BF16 && !throughput && e->trunk_variant == 4 && rows <= trunk_pp_cap1(e->n_sm) &&
+           rows <= 544;
 }
 
 int check_search_args(uttt_engine* e, int n_roots, int sims, int batch) {
@@ -242,7 +257,8 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         ealloc(e, &t.hist_final, G) || ealloc(e, &e->policy, S * cfg->max_batch * 81) ||
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
         ealloc(e, &e->headfeat, R * 243) || ealloc(e, &e->act_a, R * 81 * 128) || ealloc(e, &e->act_b, R * 81 * 128) ||
-        ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128 + 64 + 8 + 16)) {
+        ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128 + 64 + 8 + 16) ||
+        ealloc(e, &e->slot_flags, S)) {
         uttt_destroy(e);
         return 1;
     }
@@ -498,7 +514,7 @@ int uttt_mcts_begin(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int3
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     TreeParams& t = e->tp;
     t.n_trees = n_roots; t.sims = sims; t.batch = batch; t.mode = MODE_SEARCH; t.flags = 0;
-    t.parity = 0; t.row_stride = 1; t.copy_stride = 0;
+    t.parity = 0; t.row_stride = 1; t.copy_stride = 0; t.slot_flags = nullptr;
     e->s_n_roots = n_roots; e->s_sims = sims; e->s_batch = batch; e->s_round = 0; e->s_pending = 0;
     e->s_per_copy = 0; e->s_have_results = 0;
     if (n_roots == 0) return 0;
@@ -583,6 +599,13 @@ int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int
     // rounds are enqueued without host synchronisation; the tree kernel ignores finished trees.
     // Upper bound on rounds: every round retires >= 1 simulation of every unfinished tree (+ root evaluation).
     const int rows = tp ? n_roots * batch : n_roots;
+    EvalBufs bufs = bufs_of(e, 0, 0);
+    if (slot_mode_applies(e, evaluator, tp, rows)) {
+        UTTT_CUDA_OK(cudaMemsetAsync(e->slot_flags, 0, (size_t)n_roots, e->stream));
+        t.slot_flags = e->slot_flags;
+        bufs.slot_flags = e->slot_flags;
+        bufs.n_slots = n_roots;
+    }
     int max_rounds = sims + 3;
     int r = 0;
     while (r < max_rounds) {
@@ -590,7 +613,7 @@ int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int
         for (; r < stop; r++) {
             t.parity = r & 1;
             UTTT_CUDA_OK(tp ? launch_tree_tp_round(t, e->stream) : launch_tree_round(t, e->stream));
-            if (run_evaluator(e, bufs_of(e, 0, 0), evaluator, t.nn_count + t.parity, rows, e->stream, nullptr)) return 1;
+            if (run_evaluator(e, bufs, evaluator, t.nn_count + t.parity, rows, e->stream, nullptr)) return 1;
         }
         UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + ((r - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost,
                                      e->stream));
@@ -654,6 +677,8 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     t.sims = sims; t.batch = batch; t.mode = MODE_SELFPLAY; t.flags = flags;
     t.parity = 0; t.row_stride = 1; t.copy_stride = 0;
     t.seed = seed; t.game0 = game0; t.n_games = n_games;
+    const bool slots = slot_mode_applies(e, evaluator, tp, n_trees * rows_per_tree);
+    t.slot_flags = slots ? e->slot_flags : nullptr;
     // Two lanes (halves of the slots) run on two streams: each lane is the sequential chain
     // tree_round -> conv_input -> trunk -> heads, so one lane's tree/heads work runs in the shadow of the
     // other lane's trunk (the tree blocks fit beside a trunk CTA on an SM).  Lanes share only the atomic
@@ -668,6 +693,7 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
         lane_trees[l] = (l == n_lanes - 1) ? n_trees - (int)first : n_trees / n_lanes;
         TreeParams p = t;
         p.n_trees = lane_trees[l];
+        p.slot0 = (int32_t)first;
         p.root += first; p.leaf_state += first; p.ctl += first; p.path += first * PATH_CAP;
         p.nodes += first * (size_t)e->node_cap;
         size_t first_row = first * (size_t)e->rows_per_slot;
@@ -679,7 +705,9 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
         p.value = e->value + first * e->cfg.max_batch;
         lane_tp[l] = p;
         lane_bufs[l] = bufs_of(e, first, l);
+        if (slots) { lane_bufs[l].slot_flags = e->slot_flags; lane_bufs[l].n_slots = n_trees; }
     }
+    if (slots) UTTT_CUDA_OK(cudaMemsetAsync(e->slot_flags, 0, (size_t)n_trees, s));
     UTTT_CUDA_OK(cudaMemsetAsync(t.counters, 0, 8 * sizeof(unsigned long long), s));
     UTTT_CUDA_OK(cudaMemsetAsync(t.hist_len, 0, (size_t)n_games * sizeof(int32_t), s));
     UTTT_CUDA_OK(cudaEventRecord(e->ev_fork, s));

@@ -92,7 +92,9 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                  uint4* skip,                            // [gridDim][16 panels][256 rows] fp16x8 skip connection
                  const int32_t* __restrict__ count,
                  int min_count, int max_count,           // this launch handles min_count < batch <= max_count
-                 long long* dbg) {
+                 long long* dbg,
+                 int n_pos_known = -1,                   // >= 0: the batch size (slot mode: counted from the slot flags, `count` unused)
+                 const int* src_rows = nullptr) {        // slot mode: position i of this CTA pair reads planes row src_rows[i]
     using C = Cfg<LT>;
     constexpr int LOC_TILES = C::LOC_TILES, MAX_P = C::MAX_P, PANEL_BYTES = C::PANEL_BYTES, A_BYTES = C::A_BYTES,
                   STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS,
@@ -102,7 +104,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
     const int n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
-    const int n_pos = *count;
+    const int n_pos = n_pos_known >= 0 ? n_pos_known : *count;
     if (n_pos <= min_count || n_pos > max_count) return;
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0)          // diagnostics: histogram of evaluator batch sizes (16 per bucket)
         atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 128 + min(n_pos >> 4, 63), 1ull);
@@ -208,7 +210,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
             {
                 uint4 pk = zero4;
                 if (chalf == 0 && valid) {
-                    const __nv_bfloat16* px = planes + (size_t)gpos * 243 + (size_t)(r * 9 + c);
+                    const __nv_bfloat16* px = planes + (size_t)(src_rows ? src_rows[pos] : gpos) * 243 + (size_t)(r * 9 + c);
                     uint32_t x0 = (uint32_t)__bfloat16_as_ushort(px[0]), x1 = (uint32_t)__bfloat16_as_ushort(px[81]),
                              x2 = (uint32_t)__bfloat16_as_ushort(px[162]);
                     pk = make_uint4(x0 | (x1 << 16), x2, 0u, 0u);

@@ -130,9 +130,11 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_begin_kernel(TreePa
     c.ply = 0; c.game = 0; c.game_idx = -1; c.nn_row = 0; c.pad = 0;
     PackedState rs;
     if (P.mode == MODE_SELFPLAY) {
-        unsigned long long g = 0;
-        if (lane == 0) g = atomicAdd(P.counters + 0, 1ull);
-        g = __shfl_sync(FULL, g, 0);
+        // the first games go to the slots in slot order (not in arrival order at an atomic counter: which game a slot
+        // plays decides its row in the evaluator batch, and a run should be reproducible); later games are claimed from
+        // counters[0] as slots finish
+        if (t == 0 && lane == 0) atomicAdd(P.counters + 0, (unsigned long long)P.n_trees);
+        unsigned long long g = (unsigned long long)(P.slot0 + t);
         if ((int64_t)g >= P.n_games) {
             c.phase = PHASE_DONE;
             if (lane == 0) P.ctl[t] = c;
@@ -172,7 +174,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
 
     if (c.phase == PHASE_PENDING) {
         apply_leaf(P, T, c, warp_load_state_finish(leaf_raw), lane);
-        if (c.phase == PHASE_DONE) { if (lane == 0) P.ctl[t] = c; return; }
+        if (c.phase == PHASE_DONE) {
+            if (lane == 0) { P.ctl[t] = c; if (P.slot_flags) P.slot_flags[t] = 0; }
+            return;
+        }
         c.phase = PHASE_SEARCH;
     }
 
@@ -300,12 +305,12 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
 
         // ---------------- queue the leaf for the evaluator; fused leaf gather (cpp/uttt_game.cpp:244-280)
         int k = min(P.batch, c.sims_left);                            // cpp/uttt_mcts.cpp:127 flush rule
-        int row = 0;
+        int row = t;                                                  // slot mode: the leaf stays in its tree's row
         if (lane == 0) {
-            row = atomicAdd(P.nn_count + P.parity, 1);
+            if (!P.slot_flags) row = atomicAdd(P.nn_count + P.parity, 1);
             atomicAdd(P.counters + 4, 1ull);
         }
-        row = __shfl_sync(FULL, row, 0);
+        if (!P.slot_flags) row = __shfl_sync(FULL, row, 0);
         warp_store_state(P.nn_states + row, st, lane);
         warp_store_state(P.leaf_state + t, st, lane);
         if (lane == 0) { P.nn_tree[row] = t; P.nn_k[row] = k; }
@@ -316,7 +321,10 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
         c.path_len = plen;
         break;
     }
-    if (lane == 0) P.ctl[t] = c;
+    if (lane == 0) {
+        P.ctl[t] = c;
+        if (P.slot_flags) P.slot_flags[t] = (c.phase == PHASE_PENDING) ? 1 : 0;
+    }
     if (P.dbg_tree && lane == 0) {
         unsigned long long dt = (unsigned long long)(clock64() - t_start);
         unsigned long long* d = P.dbg_tree + 3 * (min(n_terminal, 7) + dbg_moved);
