@@ -305,7 +305,7 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of trunk_auto_kernel at a
                          # batch of 500 positions (profiles/r1_trunkpp_full.md): weights 9.4 MB (+ the per-CTA-half copy),
                          # planes, head features, policy / value rows; activations and the skip connection never reach DRAM
-                         "traffic": 15.13e6 if args.numerics == "bf16" else None,
+                         "traffic": 15.18e6 if args.numerics == "bf16" else None,
                          "traffic_unit": "bytes per launch (tensor-bound kernel: informational)",
                          "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                          "flop_per_launch": evals * TRUNK_FLOP_PER_POSITION / max(trunk_launches, 1),

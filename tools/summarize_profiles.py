@@ -67,8 +67,7 @@ def full(name):
     hdr, units = rows[0], rows[1]
     with open(os.path.join(P, "%s_%s_full.md" % (tag, name)), "w") as f:
         f.write("# ncu --set full, %s kernel, round %s\n\n" % (name, tag))
-        f.write("`ncu --set full --clock-control none --import-source on -k regex:<kernel> ...` on tools/trunk_timeline.py "
-                "(trunk: steady batch) / tools/prof_selfplay.py --games 500 (tree)\n\n")
+        f.write("`ncu --set full --clock-control none --import-source on -k regex:<kernel> ...` (commands: tools/gpu_round.sh)\n\n")
         seen = set()
         for r in rows[2:]:
             kname = r[hdr.index("Kernel Name")].split("(")[0]
@@ -88,7 +87,8 @@ launches()
 full("trunk1")     # trunk_tc_kernel     (one CTA per group; batch of 740 positions; UTTT_TRUNK=1/2 only)
 full("trunk2")     # trunk_auto_kernel -> trunk_tc2_body<2> (CTA pair per group, 2 tiles per CTA; batch of 345 positions)
 full("trunk3")     # trunk_tc2_kernel<3> (CTA pair per group, 3 tiles per CTA; batch of 500 positions; UTTT_TRUNK=2 only)
-full("trunkpp")    # trunk_auto_kernel -> trunk_pp_body<1> (two groups in flight, cta_group::2; batch of 500 positions) + heads FC tail
+full("trunkpp")    # trunk_auto_kernel, launch 200 of a 500-game cycle (slot mode, ~495 positions): trunk_pp_body<1> (two groups in
+                   # flight, cta_group::2) + heads FC tail
 full("heads")      # heads_fc_kernel (standalone form of the heads' FC layers; 500 positions, warm L2)
 full("tree")
 full("rules")      # step / legal / encode / gather_planes / playout kernels at 2^22 (2^20) states (tools/prof_rules.py 22)
