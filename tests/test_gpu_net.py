@@ -208,6 +208,11 @@ def test_self_play_writes_reference_history_file(setup, tmp_path, monkeypatch):
     xs2, ps2, vs2 = self_play_cpp.load_packed_history(path.replace(".history", ".packed.npz"))
     assert (xs2 == xs).all() and np.allclose(ps2, ps, atol=1e-7) and (vs2 == vs).all()
     assert os.path.getsize(path.replace(".history", ".packed.npz")) < os.path.getsize(path) / 10
+    # ... and the trainer drop-in prefers it over the pickle (same tensors either way)
+    import train_network as tn
+    a = tn.load_tensors()
+    b = tn.history_to_tensors(tn.load_data())
+    assert a[0].is_cuda and torch.equal(a[0], b[0]) and torch.allclose(a[1], b[1], atol=1e-7) and torch.equal(a[2], b[2])
     # the tensor feed gives the same layout without the pickle
     np.random.seed(7)
     x, p, v = self_play_cpp.history_tensors(torch.load("./model/best.pth", weights_only=True) and _load_best(), 24)

@@ -180,9 +180,23 @@ def train_tensors(model, xs, y_policies, y_values, epochs=None, batch_size=None,
     return loop(model, xs, y_policies, y_values, epochs, batch_size, bf16, log)
 
 
+def load_tensors():
+    """the newest cycle's samples as device tensors: from the packed sidecar `<timestamp>.packed.npz` of the newest
+    `.history` file if self-play wrote one (self_play_cpp.SP_WRITE_PACKED; 357 B per sample, planes re-encoded on the
+    GPU), else from the reference's pickle itself"""
+    history_path = sorted(Path("./data").glob("*.history"))[-1]
+    sidecar = Path(str(history_path).replace(".history", ".packed.npz"))
+    if sidecar.exists() and device.type == "cuda":
+        from self_play_cpp import load_packed_history
+        xs, pis, zs = load_packed_history(str(sidecar))
+        return (torch.from_numpy(xs).to(device), torch.from_numpy(pis).to(device),
+                torch.from_numpy(zs.astype(np.float32)).reshape(-1, 1).to(device))
+    return history_to_tensors(load_data())
+
+
 def train_network():
     """train_network.py:41-121"""
-    xs, y_policies, y_values = history_to_tensors(load_data())
+    xs, y_policies, y_values = load_tensors()
     model = DualNetwork().to(device)
     model.load_state_dict(torch.load("./model/best.pth", map_location=device, weights_only=True))
     train_tensors(model, xs, y_policies, y_values)
