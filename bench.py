@@ -150,7 +150,7 @@ def main():
     ap.add_argument("--games", type=int, default=500, help="self-play games per GPU per step (SP_GAME_COUNT)")
     ap.add_argument("--sims", type=int, default=50)
     ap.add_argument("--batch", type=int, default=8)
-    ap.add_argument("--numerics", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--numerics", default="bf16", choices=["bf16", "bf16x3", "fp32"])
     ap.add_argument("--ref-moves", type=int, default=24, help="plies per step of the reference arm")
     ap.add_argument("--cpu-baseline-moves", type=int, default=96)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -183,7 +183,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    ev_kind = engine.EVAL_NET_FP32 if args.numerics == "fp32" else engine.EVAL_NET_BF16
+    ev_kind = {"fp32": engine.EVAL_NET_FP32, "bf16": engine.EVAL_NET_BF16, "bf16x3": engine.EVAL_NET_BF16X3}[args.numerics]
     eng = engine.Engine(n_slots=min(args.games, 4096), max_sims=args.sims, max_batch=args.batch,
                         max_games=args.games, device=local_rank)
     torch.manual_seed(0)

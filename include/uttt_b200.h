@@ -34,6 +34,9 @@ extern "C" {
 #define UTTT_EVAL_NET_FP32 1 /* DualNetwork forward, fp32 CUDA-core trunk ("parity" numerics)  */
 #define UTTT_EVAL_HASH     2 /* deterministic integer-hash evaluator (search parity oracle mode) */
 #define UTTT_EVAL_HOST     3 /* caller evaluates leaves (uttt_mcts_get_leaves/put_results)     */
+#define UTTT_EVAL_NET_BF16X3 4 /* DualNetwork forward, tcgen05 trunk with split-bf16 operands (hi*hi + lo*hi + hi*lo,
+                                  fp32 accumulation and skip connection): within 1e-2 of the fp32 reference forward
+                                  (dual_network.py:89-121) on random-init weights, 3x the MMAs of _BF16 */
 
 /* self-play flags */
 #define UTTT_SP_CORRECT_TERMINAL_SIGN 1 /* opt out of the reference's inverted terminal sign (cpp/uttt_mcts.cpp:19-21) */
@@ -134,7 +137,7 @@ typedef struct {
 int uttt_upload_weights_scattered(uttt_engine *e, const uttt_weights_scattered *w, int on_device);
 
 /* DualNetwork.forward on n packed states (dual_network.py:89-121 behind pv_mcts_cpp.py:37-78):
- * policy[n][81] (softmax over all 81 actions), value[n].  mode = UTTT_EVAL_NET_BF16 / _FP32. */
+ * policy[n][81] (softmax over all 81 actions), value[n].  mode = UTTT_EVAL_NET_BF16 / _BF16X3 / _FP32. */
 int uttt_net_forward(uttt_engine *e, const uint32_t *states_dev, int64_t n, int mode,
                      float *policy_dev, float *value_dev, void *stream);
 
@@ -204,6 +207,16 @@ int uttt_debug_trunk_timeline(uttt_engine *e, int64_t *out128);
 /* diagnostics: how many tensor-core trunk launches evaluated n positions, 64 buckets of 16 (bucket 63 = 1008 and
  * more), accumulated since creation or the last call with reset != 0 */
 int uttt_debug_batch_histogram(uttt_engine *e, int64_t *out64, int32_t reset);
+
+/* diagnostics for the parity tests: while enabled, uttt_mcts_search and uttt_selfplay_run* (reference-exact search only)
+ * record every evaluated leaf with the evaluator rows its tree is about to consume -- (tree, game index, ply), packed leaf
+ * state, policy[81], value -- in evaluation order; the host synchronises after every round.  `enable` also clears the log.
+ * uttt_debug_trace_read: *n_out = records; with cap >= *n_out the arrays meta[n][3], states[n][8], policy[n][81],
+ * value[n] (HOST pointers) are filled; cap = 0 only asks for the size.  Feeding these rows to the reference's
+ * UTTT::pv_mcts_scores (cpp/uttt_mcts.cpp:84-196) must reproduce the engine's scores bit for bit. */
+int uttt_debug_trace(uttt_engine *e, int enable);
+int uttt_debug_trace_read(uttt_engine *e, int64_t cap, int64_t *n_out, int32_t *meta, uint32_t *states,
+                          float *policy, float *value);
 
 #ifdef __cplusplus
 }

@@ -153,6 +153,49 @@ int ref_mcts_scores_hash(const uint32_t w[8], float temperature, int evaluate_co
     return (int)sc.size();
 }
 
+// UTTT::pv_mcts_scores fed recorded (leaf state -> policy, value) rows (see orc_pv_mcts_scores_table): entries are consumed
+// in order, the k queued copies of a leaf inside one callback share one entry.  *misses_out = leaves without an unused
+// entry + (entries left unused << 16).
+int ref_mcts_scores_table(const uint32_t w[8], float temperature, int evaluate_count, int batch_size, int n_entries,
+                          const uint32_t *states, const float *policy, const float *value, float *scores_out,
+                          int *misses_out) {
+    std::vector<uint8_t> used((size_t)n_entries, 0);
+    int misses = 0;
+    auto model = [&](const std::vector<UTTT::State> &batch) {
+        std::vector<UTTT::InferenceResult> out;
+        int last = -1;
+        uint32_t lastw[8] = {0};
+        for (const auto &s : batch) {
+            uint32_t pw[8];
+            to_packed(s, pw);
+            int e = -1;
+            if (last >= 0 && std::memcmp(pw, lastw, 28) == 0) e = last;
+            else
+                for (int j = 0; j < n_entries; j++)
+                    if (!used[j] && std::memcmp(pw, states + 8 * j, 28) == 0) { e = j; used[j] = 1; break; }
+            UTTT::InferenceResult r;
+            if (e < 0) {
+                misses++;
+                r.policy.assign(81, 1.0f / 81.0f);
+                r.value = 0.0f;
+            } else {
+                r.policy.assign(policy + 81 * e, policy + 81 * e + 81);
+                r.value = value[e];
+                last = e;
+                std::memcpy(lastw, pw, sizeof(pw));
+            }
+            out.push_back(r);
+        }
+        return out;
+    };
+    std::vector<float> sc = UTTT::pv_mcts_scores(model, from_packed(w), temperature, evaluate_count, batch_size);
+    for (size_t i = 0; i < sc.size(); i++) scores_out[i] = sc[i];
+    int unused = 0;
+    for (int j = 0; j < n_entries; j++) unused += !used[j];
+    if (misses_out) *misses_out = misses + (unused << 16);
+    return (int)sc.size();
+}
+
 void ref_boltzman(const float *xs, int n, float temperature, float *out) {
     std::vector<float> v(xs, xs + n);
     std::vector<float> r = UTTT::boltzman(v, temperature);

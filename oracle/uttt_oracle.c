@@ -443,6 +443,86 @@ int orc_pv_mcts_scores_hash(const orc_state *root, float temperature, int evalua
                               scores_out, counts_out, stats_out);
 }
 
+/* Replay evaluator: the search is fed recorded (leaf state -> policy, value) rows, e.g. the rows a GPU engine's network
+ * produced for exactly these leaves (tests/test_gpu_replay.py: "identical network outputs on both sides").  Entries are
+ * consumed in order; the k queued copies of one leaf inside a batch (cpp/uttt_mcts.cpp:121-127) share one entry. */
+typedef struct {
+    int n;
+    const uint32_t *states;   /* [n][8] packed */
+    const float *policy;      /* [n][81] */
+    const float *value;       /* [n] */
+    uint8_t *used;
+    int misses;
+} table_ctx;
+
+static void table_eval_cb(void *ctx, const orc_state *st, int n, float *pol, float *val) {
+    table_ctx *t = (table_ctx *)ctx;
+    int last = -1;
+    uint32_t lastw[8];
+    for (int i = 0; i < n; i++) {
+        uint32_t w[8];
+        orc_pack(&st[i], w);
+        int e = -1;
+        if (last >= 0 && memcmp(w, lastw, 28) == 0) e = last;
+        else
+            for (int j = 0; j < t->n; j++)
+                if (!t->used[j] && memcmp(w, t->states + 8 * j, 28) == 0) { e = j; t->used[j] = 1; break; }
+        if (e < 0) {
+            t->misses++;
+            for (int a = 0; a < 81; a++) pol[81 * i + a] = 1.0f / 81.0f;
+            val[i] = 0.0f;
+        } else {
+            memcpy(pol + 81 * i, t->policy + 81 * e, 81 * sizeof(float));
+            val[i] = t->value[e];
+            last = e;
+            memcpy(lastw, w, sizeof(w));
+        }
+    }
+}
+
+/* returns the number of root children; *misses_out = leaves that had no unused entry (+ entries left unused << 16) */
+int orc_pv_mcts_scores_table(const orc_state *root, float temperature, int evaluate_count, int batch_size, int n_entries,
+                             const uint32_t *states, const float *policy, const float *value, float *scores_out,
+                             int *counts_out, int *misses_out) {
+    table_ctx t = {n_entries, states, policy, value, (uint8_t *)calloc((size_t)(n_entries > 0 ? n_entries : 1), 1), 0};
+    int n = orc_pv_mcts_scores(table_eval_cb, &t, root, temperature, evaluate_count, batch_size, scores_out, counts_out, NULL);
+    int unused = 0;
+    for (int j = 0; j < n_entries; j++) unused += !t.used[j];
+    if (misses_out) *misses_out = t.misses + (unused << 16);
+    free(t.used);
+    return n;
+}
+
+/* the hash-evaluator search, recording every distinct evaluated leaf in order (pins the replay machinery on the CPU:
+ * replaying the record must reproduce the scores) */
+typedef struct { int cap, n; uint32_t *states; float *policy; float *value; } record_ctx;
+static void record_eval_cb(void *ctx, const orc_state *st, int n, float *pol, float *val) {
+    record_ctx *r = (record_ctx *)ctx;
+    hash_eval_cb(NULL, st, n, pol, val);
+    for (int i = 0; i < n; i++) {
+        uint32_t w[8];
+        orc_pack(&st[i], w);
+        if (i > 0) {
+            uint32_t p[8];
+            orc_pack(&st[i - 1], p);
+            if (memcmp(w, p, 28) == 0) continue;
+        }
+        if (r->n < r->cap) {
+            memcpy(r->states + 8 * r->n, w, 32);
+            memcpy(r->policy + 81 * r->n, pol + 81 * i, 81 * sizeof(float));
+            r->value[r->n] = val[i];
+        }
+        r->n++;
+    }
+}
+int orc_pv_mcts_scores_hash_record(const orc_state *root, float temperature, int evaluate_count, int batch_size, int cap,
+                                   uint32_t *states, float *policy, float *value, int *n_entries_out, float *scores_out) {
+    record_ctx r = {cap, 0, states, policy, value};
+    int n = orc_pv_mcts_scores(record_eval_cb, &r, root, temperature, evaluate_count, batch_size, scores_out, NULL, NULL);
+    *n_entries_out = r.n;
+    return n;
+}
+
 /* ------------------------------------------------------------ bulk drivers */
 static inline uint64_t fnv64(uint64_t h, uint32_t x) {
     return (h ^ (uint64_t)x) * 0x100000001B3ull;

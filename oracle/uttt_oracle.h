@@ -56,6 +56,11 @@ uint32_t orc_state_hash(const orc_state *s);
 void     orc_hash_eval(const orc_state *s, float policy[81], float *value);
 
 /* evaluator callback: fills policy[81], value for each of n states */
+int orc_pv_mcts_scores_table(const orc_state *root, float temperature, int evaluate_count, int batch_size, int n_entries,
+                             const uint32_t *states, const float *policy, const float *value, float *scores_out,
+                             int *counts_out, int *misses_out);
+int orc_pv_mcts_scores_hash_record(const orc_state *root, float temperature, int evaluate_count, int batch_size, int cap,
+                                   uint32_t *states, float *policy, float *value, int *n_entries_out, float *scores_out);
 typedef void (*orc_eval_fn)(void *ctx, const orc_state *states, int n,
                             float *policies /* n*81 */, float *values /* n */);
 

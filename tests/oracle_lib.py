@@ -67,6 +67,12 @@ def oracle():
                                   C.POINTER(C.c_int), u8p]
         L.orc_selfplay_hash.argtypes = [C.c_uint32, C.c_uint64, C.c_int, C.c_int, u32p, u16p, u8p, i8p]
         L.orc_selfplay_hash.restype = C.c_int
+        L.orc_pv_mcts_scores_table.argtypes = [SP, C.c_float, C.c_int, C.c_int, C.c_int, u32p, f32p, f32p, f32p, i32p,
+                                               C.POINTER(C.c_int)]
+        L.orc_pv_mcts_scores_table.restype = C.c_int
+        L.orc_pv_mcts_scores_hash_record.argtypes = [SP, C.c_float, C.c_int, C.c_int, C.c_int, u32p, f32p, f32p,
+                                                     C.POINTER(C.c_int), f32p]
+        L.orc_pv_mcts_scores_hash_record.restype = C.c_int
         L.orc_az_search_hash.argtypes = [SP, C.c_int, i32p]
         L.orc_az_search_hash.restype = C.c_int
         _oracle = L
@@ -88,6 +94,9 @@ def ref():
         L.ref_state_to_string.restype = C.c_int
         L.ref_mcts_scores_hash.argtypes = [u32p, C.c_float, C.c_int, C.c_int, f32p, i32p]
         L.ref_mcts_scores_hash.restype = C.c_int
+        L.ref_mcts_scores_table.argtypes = [u32p, C.c_float, C.c_int, C.c_int, C.c_int, u32p, f32p, f32p, f32p,
+                                            C.POINTER(C.c_int)]
+        L.ref_mcts_scores_table.restype = C.c_int
         L.ref_boltzman.argtypes = [f32p, C.c_int, C.c_float, f32p]
         L.ref_selfplay_hash.argtypes = [C.c_uint32, C.c_uint64, C.c_int, C.c_int, u32p, u16p, u8p, i8p]
         L.ref_selfplay_hash.restype = C.c_int
@@ -155,6 +164,43 @@ def ref_mcts(w, temperature, sims, batch):
     st = np.zeros(2, np.int32)
     n = ref().ref_mcts_scores_hash(np.ascontiguousarray(w, dtype=np.uint32), temperature, sims, batch, sc, st)
     return sc[:n].copy(), st
+
+
+def table_mcts(w, temperature, sims, batch, states, policy, value, use_ref=None):
+    """The reference search (compiled reference if it was built here, else the C restatement) fed recorded rows
+    (leaf state -> policy[81], value), consumed in order.  -> (scores, leaves without a row, rows left unused)"""
+    states = np.ascontiguousarray(states, dtype=np.uint32).reshape(-1, 8)
+    policy = np.ascontiguousarray(policy, dtype=np.float32).reshape(-1, 81)
+    value = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)
+    n = len(value)
+    if n == 0:      # ndpointer rejects empty arrays of the wrong shape: pass one dummy row that is never matched
+        states, policy, value = np.full((1, 8), 0xFFFFFFFF, np.uint32), np.zeros((1, 81), np.float32), np.zeros(1, np.float32)
+    sc = np.zeros(81, np.float32)
+    miss = C.c_int(0)
+    if use_ref is None:
+        use_ref = ref_available()
+    if use_ref:
+        m = ref().ref_mcts_scores_table(np.ascontiguousarray(w, dtype=np.uint32), temperature, sims, batch, n, states, policy,
+                                        value, sc, C.byref(miss))
+    else:
+        s = state_from_packed(w)
+        cn = np.zeros(81, np.int32)
+        m = oracle().orc_pv_mcts_scores_table(C.byref(s), temperature, sims, batch, n, states, policy, value, sc, cn,
+                                              C.byref(miss))
+    return sc[:m].copy(), miss.value & 0xFFFF, miss.value >> 16
+
+
+def record_hash_mcts(w, temperature, sims, batch, cap=4096):
+    """oracle search under the hash evaluator + the rows it evaluated, in order"""
+    s = state_from_packed(w)
+    st = np.zeros((cap, 8), np.uint32)
+    pol = np.zeros((cap, 81), np.float32)
+    val = np.zeros(cap, np.float32)
+    n = C.c_int(0)
+    sc = np.zeros(81, np.float32)
+    m = oracle().orc_pv_mcts_scores_hash_record(C.byref(s), temperature, sims, batch, cap, st, pol, val, C.byref(n), sc)
+    assert n.value <= cap
+    return sc[:m].copy(), st[:n.value], pol[:n.value], val[:n.value]
 
 
 def oracle_az_search(w, sims):

@@ -132,3 +132,24 @@ def test_oracle_vs_live_reference():
                     sc, _, _ = O.oracle_mcts(w, T, sims, batch)
                     rc, _ = O.ref_mcts(w, T, sims, batch)
                     assert sc.shape == rc.shape and (sc.view(np.uint32) == rc.view(np.uint32)).all()
+
+
+def test_replay_evaluator_reproduces_the_hash_search():
+    """The table-fed search (what tests/test_gpu_replay.py uses to replay a GPU engine's network rows through the
+    reference's UTTT::pv_mcts_scores, cpp/uttt_mcts.cpp:84-196): recording the leaves of a hash-evaluator search and
+    replaying them gives the same float scores, in the C restatement and in the compiled reference."""
+    detected = []
+    for seed, game in ((77, 0), (77, 3)):
+        sts = O.playout_states(seed, game)[0]
+        for w in sts[::7]:
+            for sims, batch, T in ((50, 8, 1.0), (50, 1, 1.0), (37, 5, 0.0), (200, 8, 1.0)):
+                sc, st, pol, val = O.record_hash_mcts(w, T, sims, batch)
+                want, _, _ = O.oracle_mcts(w, T, sims, batch)
+                assert sc.tobytes() == want.tobytes()
+                for use_ref in ([False, True] if O.ref_available() else [False]):
+                    got, miss, unused = O.table_mcts(w, T, sims, batch, st, pol, val, use_ref=use_ref)
+                    assert miss == 0 and unused == 0 and got.tobytes() == want.tobytes(), (sims, batch, T, use_ref)
+                if len(val) > 3 and T == 1.0:        # rows given to the wrong leaves change the result
+                    got, _, _ = O.table_mcts(w, T, sims, batch, st, np.roll(pol, 1, axis=0), np.roll(val, 1))
+                    detected.append(got.tobytes() != want.tobytes())
+    assert len(detected) > 20 and np.mean(detected) > 0.8, (len(detected), np.mean(detected))

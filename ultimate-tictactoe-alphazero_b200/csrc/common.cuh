@@ -130,6 +130,10 @@ struct NetWeights {
     __nv_bfloat16* res_w_2sm;        // [32*9 stages][2][8 blocks]...
     __nv_bfloat16* conv_in_w_2sm;    // [2 stages][2][8 taps]... (16 tap slots, 9 used)
     __nv_bfloat16* bias_blk_2sm;     // [33][2][1 block]...
+    // split-bf16 ("bf16x3") copies for trunk_x3_kernel: every block is followed by its lo part, lo = bf16(w - hi)
+    __nv_bfloat16* res_w_x3;         // [32][72 K-blocks][hi, lo][2 k-panels][128][8]
+    __nv_bfloat16* conv_in_w_x3;     // [9 taps][hi, lo][2][128][8]
+    __nv_bfloat16* bias_blk_x3;      // [33][2][128][8]: shift as three bf16 terms in k = 0, 1, 2
     float* head_w;                   // [3][128] policy conv (2 rows) + value conv, BN scale folded; [384..386] BN shifts
     // heads (fp32): policy conv [2][128] + shift[2], fc [81][162] + b; value conv [128] + shift, fc1 [256][81]+b, fc2 [256]+b
     float* pol_conv_w; float* pol_conv_b; float* pol_fc_w; float* pol_fc_b;
@@ -145,19 +149,17 @@ cudaError_t launch_trunk_fp32(const NetWeights& w, const __nv_bfloat16* planes, 
                               float* act_a, float* act_b, cudaStream_t s);
 // planes: network input [rows][3][81] bf16; headfeat: [rows][243] output of the heads' 1x1 convs (computed in the
 // trunk's last epilogue); resid: per-CTA fp16 skip panels
-cudaError_t launch_trunk_tc(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
-                            int max_rows, float* resid, int n_sm, cudaStream_t s, long long* dbg = nullptr,
-                            int min_count = 0);
 cudaError_t launch_heads_fc(const NetWeights& w, const float* headfeat, const int32_t* count, int max_rows, float* policy,
                             float* value, int row_stride, cudaStream_t s);
 cudaError_t launch_heads(const NetWeights& w, const float* act_f32, const __nv_bfloat16* act_bf16,
                          const int32_t* count, int max_rows, float* policy, float* value, int row_stride,
                          cudaStream_t s);
 // cluster-of-2 variant (net_tc2.cu): one group of positions per CTA pair; skip: [n_sm][16][256] fp16x8
-cudaError_t launch_trunk_tc2(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
-                             int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg = nullptr);
 cudaError_t trunk_tc2_init();
-// only the 5-positions-per-pair instantiation (batches up to trunk_tc2_small_capacity); larger ones go to launch_trunk_pp
+// split-bf16 numerics (UTTT_EVAL_NET_BF16X3): any batch size in one launch; skip: [n_sm][16][256] fp32x8
+cudaError_t launch_trunk_x3(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
+                            int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg);
+// batches up to trunk_tc2_small_capacity (one group of <= 5 positions per CTA pair); larger ones go to launch_trunk_pp
 cudaError_t launch_trunk_tc2_small(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
                                    int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg);
 int trunk_tc2_small_capacity(int n_sm);
@@ -175,8 +177,5 @@ cudaError_t launch_trunk_auto(const NetWeights& w, const __nv_bfloat16* planes, 
                               float* skip, int n_sm, cudaStream_t s, long long* dbg, float* policy, float* value,
                               const uint8_t* slot_flags = nullptr, int n_slots = 0);
 cudaError_t trunk_auto_init();
-int trunk_tc2_capacity(int n_sm);    // largest batch the cluster variant evaluates in one wave
-int trunk_tc_smem_bytes();
-cudaError_t trunk_tc_init();
 
 }  // namespace uttt

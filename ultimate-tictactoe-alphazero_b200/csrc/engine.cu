@@ -30,12 +30,14 @@ constexpr int N_WINDOWS = 2;           // self-play keeps two windows of CHECK_E
 constexpr int EV_POOL = N_WINDOWS * CHECK_EVERY * 4 * N_LANES;
 
 __global__ void set_int_kernel(int32_t* p, int32_t v) { *p = v; }
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
 // BatchNorm folding + repacking of the 32 residual 3x3 convolutions on the device:
 // raw (32)(co,ci,ky,kx) fp32 + bn (32)(4)(128) -> fp32 [l][tap][ci][co], bias [l][co], bf16 [l][tap][ci/8][co][ci%8]
+// and the split-bf16 copy [l][K-block][hi, lo][ci/8 % 2][co][ci%8] with lo = bf16(w - hi)
 __global__ void __launch_bounds__(256) pack_res_kernel(const float* __restrict__ raw, const float* __restrict__ bn,
                                                        float* __restrict__ w32, float* __restrict__ b32,
-                                                       __nv_bfloat16* __restrict__ w16) {
+                                                       __nv_bfloat16* __restrict__ w16, __nv_bfloat16* __restrict__ w16x3) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;      // index into raw
     if (i >= (size_t)32 * 128 * 128 * 9) return;
     int tap = (int)(i % 9);
@@ -51,7 +53,11 @@ __global__ void __launch_bounds__(256) pack_res_kernel(const float* __restrict__
     w32[(((size_t)l * 9 + tap) * 128 + ci) * 128 + co] = val;
     // tensor-core copy: 72 K-blocks per layer in the order of tcx::kblock_of, each [2 panels][128 co][8 ci]
     int blk = tcx::kblock_of(tap, ci / 16);
-    w16[((((size_t)l * 72 + blk) * 2 + ((ci / 8) & 1)) * 128 + co) * 8 + (ci % 8)] = __float2bfloat16(val);
+    const __nv_bfloat16 hi = __float2bfloat16(val);
+    w16[((((size_t)l * 72 + blk) * 2 + ((ci / 8) & 1)) * 128 + co) * 8 + (ci % 8)] = hi;
+    const size_t x3 = (((((size_t)l * 72 + blk) * 2) * 2 + ((ci / 8) & 1)) * 128 + co) * 8 + (ci % 8);
+    w16x3[x3] = hi;
+    w16x3[x3 + 2 * 128 * 8] = __float2bfloat16(__fsub_rn(val, __bfloat162float(hi)));
     if (ci == 0 && tap == 0) b32[l * 128 + co] = __fsub_rn(beta, __fmul_rn(m, sc));
 }
 
@@ -82,9 +88,8 @@ struct uttt_engine {
     int prof_level;         // self-play kernel timing: 2 = tree / trunk / heads events every round, 1 = trunk only, 0 = none
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
     int trunk_variant;      // 4 (default): CTA pair per group (net_tc2) up to 370 positions, two groups in flight per pair with
-                            // cta_group::2 MMAs (net_pp) above, chosen on the device inside ONE launch (net_auto.cu); 3: the
-                            // same two kernels as separate launches; for comparison 2: net_tc2 (2 or 3 tiles per CTA) up to
-                            // 518 positions and net_tc above, 1: one CTA per group (net_tc) only
+                            // cta_group::2 MMAs (net_pp) above, chosen on the device inside ONE launch (net_auto.cu); 3 (kept
+                            // for comparison): the same two bodies as separate launches
     NetWeights w;
     float* raw_res;         // staging for the raw residual conv weights / bn of an upload
     float* raw_res_bn;
@@ -97,6 +102,11 @@ struct uttt_engine {
     double prof_ms[4];
     int64_t prof_launches[4];
     std::vector<void*> allocs;
+    // diagnostics (uttt_debug_trace): every evaluated leaf of the reference-exact search with the rows its tree is about to
+    // consume -- what tests/test_gpu_replay.py feeds to the CPU reference search
+    bool trace_on;
+    struct TraceRec { int32_t tree, game_idx, ply; float value; uint32_t state[8]; float policy[81]; };
+    std::vector<TraceRec> trace;
 };
 
 namespace {
@@ -150,6 +160,12 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         if (ev3) cudaEventRecord(ev3[0], s);
         UTTT_CUDA_OK(launch_trunk_fp32(e->w, b.nn_planes, count, max_rows, b.act_a, b.act_b, s));
         e->prof_launches[1] += 1 + 2 * NET_BLOCKS;
+    } else if (evaluator == UTTT_EVAL_NET_BF16X3) {
+        // split-bf16 numerics: one launch for any batch (groups of <= 5 positions per CTA pair, several waves if needed);
+        // the heads' FC layers follow as their own kernel (1 % of a round here: the trunk issues 3x the MMAs)
+        if (ev3) cudaEventRecord(ev3[0], s);
+        UTTT_CUDA_OK(launch_trunk_x3(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
+        e->prof_launches[1] += 1;
     } else if (evaluator == UTTT_EVAL_NET_BF16) {
         // conv_input runs inside the trunk kernels (tensor pipe, "layer -1").  The queue length is only known on the
         // device: small batches (one wave of CTA pairs) are latency-bound -> one group per pair with the next layer
@@ -168,20 +184,13 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
                                            b.n_slots));
             if (!heads_fused)
                 UTTT_CUDA_OK(launch_trunk_pp_large(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
-        } else if (e->trunk_variant == 3) {
-            // up to one wave of 5-position groups: cluster kernel whose next layer overlaps the epilogue; above: the
+        } else {
+            // UTTT_TRUNK=3 (comparison): up to one wave of 5-position groups: cluster kernel whose next layer overlaps the epilogue; above: the
             // two-groups-in-flight kernel (net_pp.cu)
             const int cap = trunk_tc2_small_capacity(e->n_sm);
             UTTT_CUDA_OK(launch_trunk_tc2_small(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
             if (max_rows > cap)
                 UTTT_CUDA_OK(launch_trunk_pp(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg, cap));
-        } else if (e->trunk_variant == 2) {
-            if (max_rows > trunk_tc2_capacity(e->n_sm))
-                UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg,
-                                             trunk_tc2_capacity(e->n_sm)));
-            UTTT_CUDA_OK(launch_trunk_tc2(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
-        } else {
-            UTTT_CUDA_OK(launch_trunk_tc(e->w, b.nn_planes, b.headfeat, count, max_rows, b.resid, e->n_sm, s, e->tc_dbg));
         }
         e->prof_launches[1] += 1;
     } else {
@@ -192,12 +201,55 @@ int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_
         if (ev3 && e->prof_level >= 2) cudaEventRecord(ev3[2], s);
         return 0;
     }
-    if (evaluator == UTTT_EVAL_NET_BF16)
+    if (evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_BF16X3)
         UTTT_CUDA_OK(launch_heads_fc(e->w, b.headfeat, count, max_rows, b.policy, b.value, 1, s));
     else
         UTTT_CUDA_OK(launch_heads(e->w, b.act_a, nullptr, count, max_rows, b.policy, b.value, 1, s));
     e->prof_launches[2] += 1;
     if (ev3 && e->prof_level >= 2) cudaEventRecord(ev3[2], s);
+    return 0;
+}
+
+// uttt_debug_trace: after a round's evaluator, record (tree, game, ply, leaf state, policy row, value) of every queued leaf.
+// Synchronises the stream (diagnostics only).
+int trace_round(uttt_engine* e, const TreeParams& p, const EvalBufs& b, const int32_t* count, cudaStream_t s) {
+    UTTT_CUDA_OK(cudaStreamSynchronize(s));
+    int n_rows = 0;
+    std::vector<uint8_t> flags;
+    std::vector<int32_t> trees;
+    if (b.slot_flags) {
+        n_rows = b.n_slots;
+        flags.resize((size_t)n_rows);
+        UTTT_CUDA_OK(cudaMemcpy(flags.data(), b.slot_flags, (size_t)n_rows, cudaMemcpyDeviceToHost));
+    } else {
+        int32_t n = 0;
+        UTTT_CUDA_OK(cudaMemcpy(&n, count, sizeof(n), cudaMemcpyDeviceToHost));
+        n_rows = n;
+        trees.resize((size_t)n_rows);
+        if (n_rows) UTTT_CUDA_OK(cudaMemcpy(trees.data(), p.nn_tree, (size_t)n_rows * 4, cudaMemcpyDeviceToHost));
+    }
+    if (n_rows == 0) return 0;
+    std::vector<uint32_t> st((size_t)n_rows * 8);
+    std::vector<float> pol((size_t)n_rows * 81), val((size_t)n_rows);
+    std::vector<TreeCtl> ctl((size_t)p.n_trees);
+    UTTT_CUDA_OK(cudaMemcpy(st.data(), b.nn_states, st.size() * 4, cudaMemcpyDeviceToHost));
+    UTTT_CUDA_OK(cudaMemcpy(pol.data(), b.policy, pol.size() * 4, cudaMemcpyDeviceToHost));
+    UTTT_CUDA_OK(cudaMemcpy(val.data(), b.value, val.size() * 4, cudaMemcpyDeviceToHost));
+    UTTT_CUDA_OK(cudaMemcpy(ctl.data(), p.ctl, ctl.size() * sizeof(TreeCtl), cudaMemcpyDeviceToHost));
+    for (int r = 0; r < n_rows; r++) {
+        if (b.slot_flags && !flags[r]) continue;
+        const int t = b.slot_flags ? r : trees[r];
+        UTTT_CHECK(t >= 0 && t < p.n_trees && ctl[t].phase == PHASE_PENDING && ctl[t].nn_row == r,
+                   "trace: row %d does not belong to a pending tree", r);
+        uttt_engine::TraceRec rec;
+        rec.tree = p.slot0 + t;
+        rec.game_idx = (p.mode == MODE_SELFPLAY) ? ctl[t].game_idx : p.slot0 + t;
+        rec.ply = (p.mode == MODE_SELFPLAY) ? ctl[t].ply : 0;
+        rec.value = val[r];
+        memcpy(rec.state, st.data() + (size_t)r * 8, 32);
+        memcpy(rec.policy, pol.data() + (size_t)r * 81, 81 * 4);
+        e->trace.push_back(rec);
+    }
     return 0;
 }
 
@@ -233,6 +285,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     memset(&e->tp, 0, sizeof(e->tp));
     memset(&e->w, 0, sizeof(e->w));
     e->cfg = *cfg;
+    e->trace_on = false;
     e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 4;
     e->prof_level = getenv("UTTT_PROFILE") ? atoi(getenv("UTTT_PROFILE")) : 1;
     e->lane_threshold = getenv("UTTT_LANE_THRESHOLD") ? atoi(getenv("UTTT_LANE_THRESHOLD")) : 1024;
@@ -292,7 +345,7 @@ int uttt_destroy(uttt_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
-    float* wp[] = {e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, e->w.head_w, e->w.pol_conv_w,
+    float* wp[] = {(float*)e->w.res_w_x3, (float*)e->w.conv_in_w_x3, (float*)e->w.bias_blk_x3, e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, e->w.head_w, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b, e->w.heads_pack};
     for (float* p : wp) if (p) cudaFree(p);
@@ -361,6 +414,7 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
         UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w, n_res * sizeof(float)));
         UTTT_CUDA_OK(cudaMalloc((void**)&W.res_b, 32 * 128 * sizeof(float)));
         UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_bf16, n_res * sizeof(__nv_bfloat16)));
+        UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_x3, 2 * n_res * sizeof(__nv_bfloat16)));
     }
     cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (res_tab) {
@@ -380,7 +434,7 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
         UTTT_CUDA_OK(cudaMemcpyAsync(e->raw_res_bn, w->res_bn, n_rbn * sizeof(float), kind, e->stream));
     }
     pack_res_kernel<<<ceil_div((int64_t)n_res, 256), 256, 0, e->stream>>>(e->raw_res, e->raw_res_bn, W.res_w, W.res_b,
-                                                                         W.res_w_bf16);
+                                                                         W.res_w_bf16, W.res_w_x3);
     UTTT_CUDA_OK(cudaGetLastError());
 
     std::vector<float> sc, sh;
@@ -433,6 +487,32 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
             }
         if (!W.bias_blk) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_blk, bb.size() * sizeof(__nv_bfloat16)));
         UTTT_CUDA_OK(cudaMemcpy(W.bias_blk, bb.data(), bb.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        // split-bf16 trunk: conv_input as [9 taps][hi, lo][2][128][8], the shifts as three bf16 terms (k = 0, 1, 2)
+        {
+            std::vector<__nv_bfloat16> cx((size_t)9 * 2 * 2 * 128 * 8, __float2bfloat16(0.0f));
+            for (int tap = 0; tap < 9; tap++)
+                for (int ci = 0; ci < 3; ci++)
+                    for (int co = 0; co < 128; co++) {
+                        float v = ci_w[(tap * 3 + ci) * 128 + co];
+                        __nv_bfloat16 hi = __float2bfloat16(v);
+                        cx[(((size_t)tap * 2 + 0) * 2 * 128 + co) * 8 + ci] = hi;
+                        cx[(((size_t)tap * 2 + 1) * 2 * 128 + co) * 8 + ci] = __float2bfloat16(v - __bfloat162float(hi));
+                    }
+            if (!W.conv_in_w_x3) UTTT_CUDA_OK(cudaMalloc((void**)&W.conv_in_w_x3, cx.size() * sizeof(__nv_bfloat16)));
+            UTTT_CUDA_OK(cudaMemcpy(W.conv_in_w_x3, cx.data(), cx.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+            std::vector<__nv_bfloat16> b3((size_t)33 * 2 * 128 * 8, __float2bfloat16(0.0f));
+            for (int l = 0; l < 33; l++)
+                for (int co = 0; co < 128; co++) {
+                    float b = ball[l * 128 + co];
+                    for (int k = 0; k < 3; k++) {
+                        __nv_bfloat16 t = __float2bfloat16(b);
+                        b3[((size_t)l * 2 * 128 + co) * 8 + k] = t;
+                        b -= __bfloat162float(t);
+                    }
+                }
+            if (!W.bias_blk_x3) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_blk_x3, b3.size() * sizeof(__nv_bfloat16)));
+            UTTT_CUDA_OK(cudaMemcpy(W.bias_blk_x3, b3.data(), b3.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+        }
         // per-CTA halves of the three B-operand arrays for the cta_group::2 trunk
         const size_t blk = 2 * 128 * 8;
         if (!W.res_w_2sm) UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_2sm, (size_t)32 * 72 * blk * sizeof(__nv_bfloat16)));
@@ -473,7 +553,6 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
         to_device(&W.val_fc2_w, v2w) || to_device(&W.val_fc2_b, v2b))
         return 1;
     UTTT_CUDA_OK(cudaStreamSynchronize(e->stream));
-    UTTT_CUDA_OK(trunk_tc_init());
     UTTT_CUDA_OK(trunk_tc2_init());
     UTTT_CUDA_OK(trunk_pp_init());
     UTTT_CUDA_OK(trunk_auto_init());
@@ -493,7 +572,8 @@ int uttt_upload_weights_scattered(uttt_engine* e, const uttt_weights_scattered* 
 int uttt_net_forward(uttt_engine* e, const uint32_t* states_dev, int64_t n, int mode, float* policy_dev,
                      float* value_dev, void* stream) {
     UTTT_CHECK(e && (n == 0 || (states_dev && policy_dev && value_dev)), "null argument");
-    UTTT_CHECK(mode == UTTT_EVAL_NET_BF16 || mode == UTTT_EVAL_NET_FP32, "mode must be UTTT_EVAL_NET_BF16 or _FP32");
+    UTTT_CHECK(mode == UTTT_EVAL_NET_BF16 || mode == UTTT_EVAL_NET_FP32 || mode == UTTT_EVAL_NET_BF16X3,
+               "mode must be UTTT_EVAL_NET_BF16, _BF16X3 or _FP32");
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
     for (int64_t off = 0; off < n; off += e->cfg.n_slots) {
@@ -587,7 +667,8 @@ int uttt_mcts_finish(uttt_engine* e, float temperature, float* scores, int32_t* 
 int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int32_t sims, int32_t batch,
                      float temperature, int32_t evaluator, int32_t flags, float* scores, int32_t* counts,
                      int32_t* n_scores) {
-    UTTT_CHECK(evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_FP32 || evaluator == UTTT_EVAL_HASH,
+    UTTT_CHECK(evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_FP32 || evaluator == UTTT_EVAL_HASH ||
+                   evaluator == UTTT_EVAL_NET_BF16X3,
                "uttt_mcts_search needs a device evaluator; use the step-wise calls for UTTT_EVAL_HOST");
     const bool tp = (flags & UTTT_SP_THROUGHPUT) != 0;
     UTTT_CHECK(!tp || batch <= TP_MAX_LEAVES, "throughput mode: at most %d leaves per tree per round", TP_MAX_LEAVES);
@@ -614,6 +695,7 @@ int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int
             t.parity = r & 1;
             UTTT_CUDA_OK(tp ? launch_tree_tp_round(t, e->stream) : launch_tree_round(t, e->stream));
             if (run_evaluator(e, bufs, evaluator, t.nn_count + t.parity, rows, e->stream, nullptr)) return 1;
+            if (e->trace_on && !tp && trace_round(e, t, bufs, t.nn_count + t.parity, e->stream)) return 1;
         }
         UTTT_CUDA_OK(cudaMemcpyAsync(e->h_count, t.nn_count + ((r - 1) & 1), sizeof(int32_t), cudaMemcpyDeviceToHost,
                                      e->stream));
@@ -661,7 +743,8 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     UTTT_CHECK(e != nullptr, "null engine");
     UTTT_CHECK(n_games >= 0 && n_games <= e->cfg.max_games, "n_games %lld exceeds max_games %lld", (long long)n_games,
                (long long)e->cfg.max_games);
-    UTTT_CHECK(evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_FP32 || evaluator == UTTT_EVAL_HASH,
+    UTTT_CHECK(evaluator == UTTT_EVAL_NET_BF16 || evaluator == UTTT_EVAL_NET_FP32 || evaluator == UTTT_EVAL_HASH ||
+                   evaluator == UTTT_EVAL_NET_BF16X3,
                "self-play needs a device evaluator");
     int n_trees = (int)((n_games < e->cfg.n_slots) ? n_games : e->cfg.n_slots);
     if (check_search_args(e, n_trees, sims, batch)) return 1;
@@ -684,7 +767,8 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     // other lane's trunk (the tree blocks fit beside a trunk CTA on an SM).  Lanes share only the atomic
     // game/progress counters and the history buffers (disjoint rows).
     // (worth it only when half a batch still fills the machine; small batches are latency-bound)
-    const int n_lanes = (n_trees >= e->lane_threshold) ? N_LANES : 1;
+    // (slot mode addresses the evaluator rows by global slot: one lane)
+    const int n_lanes = (n_trees >= e->lane_threshold && !slots) ? N_LANES : 1;
     TreeParams lane_tp[N_LANES];
     EvalBufs lane_bufs[N_LANES];
     int lane_trees[N_LANES];
@@ -709,6 +793,9 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     }
     if (slots) UTTT_CUDA_OK(cudaMemsetAsync(e->slot_flags, 0, (size_t)n_trees, s));
     UTTT_CUDA_OK(cudaMemsetAsync(t.counters, 0, 8 * sizeof(unsigned long long), s));
+    // (counters[0] = next game to hand out: the first n_trees games are assigned by tree_begin; set here, before the lanes
+    // fork, so that no lane's begin kernel races with another lane's first recycled slot)
+    if (!tp) set_u64_kernel<<<1, 1, 0, s>>>(t.counters, (unsigned long long)n_trees);
     UTTT_CUDA_OK(cudaMemsetAsync(t.hist_len, 0, (size_t)n_games * sizeof(int32_t), s));
     UTTT_CUDA_OK(cudaEventRecord(e->ev_fork, s));
     cudaStream_t ls[N_LANES];
@@ -738,6 +825,8 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
                 if (run_evaluator(e, lane_bufs[l], evaluator, lane_tp[l].nn_count + lane_tp[l].parity,
                                   lane_trees[l] * rows_per_tree,
                                   ls[l], e->prof_level >= 1 ? ev + 1 : nullptr))
+                    return 1;
+                if (e->trace_on && !tp && trace_round(e, lane_tp[l], lane_bufs[l], lane_tp[l].nn_count + lane_tp[l].parity, ls[l]))
                     return 1;
             }
         }
@@ -866,6 +955,30 @@ int uttt_debug_batch_histogram(uttt_engine* e, int64_t* out64, int32_t reset) {
     UTTT_CUDA_OK(cudaDeviceSynchronize());
     UTTT_CUDA_OK(cudaMemcpy(out64, e->tc_dbg + 128, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
     if (reset) UTTT_CUDA_OK(cudaMemset(e->tc_dbg + 128, 0, 64 * sizeof(long long)));
+    return 0;
+}
+
+int uttt_debug_trace(uttt_engine* e, int enable) {
+    UTTT_CHECK(e != nullptr, "null engine");
+    e->trace_on = enable != 0;
+    e->trace.clear();
+    return 0;
+}
+
+int uttt_debug_trace_read(uttt_engine* e, int64_t cap, int64_t* n_out, int32_t* meta, uint32_t* states, float* policy,
+                          float* value) {
+    UTTT_CHECK(e && n_out, "null argument");
+    const int64_t n = (int64_t)e->trace.size();
+    *n_out = n;
+    if (cap <= 0) return 0;
+    UTTT_CHECK(cap >= n && meta && states && policy && value, "trace buffers too small (%lld records)", (long long)n);
+    for (int64_t i = 0; i < n; i++) {
+        const uttt_engine::TraceRec& r = e->trace[(size_t)i];
+        meta[3 * i] = r.tree; meta[3 * i + 1] = r.game_idx; meta[3 * i + 2] = r.ply;
+        memcpy(states + 8 * i, r.state, 32);
+        memcpy(policy + 81 * i, r.policy, 81 * 4);
+        value[i] = r.value;
+    }
     return 0;
 }
 

@@ -30,28 +30,35 @@ namespace tc2 {
 
 constexpr int POS_ROWS = 100;
 constexpr int LEAD = 11;
-constexpr int STAGE_BLOCKS = 8;                 // K-blocks (MMAs per tile) per weight stage.  An issuer thread pays one
-                                                // barrier wait and one commit per stage (200+ cycles each while the tensor
-                                                // pipe saturates shared memory): with 4-block stages a CTA that owns ONE tile
-                                                // (batches of up to 148 positions) was issue-bound at ~93 cycles per MMA
-constexpr int STAGE_BYTES = STAGE_BLOCKS * 4096;
-constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
-constexpr int IN_STAGES = 2;                    // conv_input: 9 taps x (K=16: 3 real channels) in 16 tap slots
-constexpr int BIAS_BYTES = 4096;                // one [2 panels][128 co][8] block: BN shift as bf16 hi + lo in k = 0, 1
-constexpr int GROUP_STAGES = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);   // every layer starts with its bias block
+constexpr int BIAS_BYTES = 4096;                // one [2 panels][128 co][8] block: BN shift as bf16 hi + lo (+ lo2) in k = 0, 1 (, 2)
 constexpr int GROUP_LAYERS = NET_LAYERS + 1;     // conv_input runs as layer -1 through the same pipeline
 constexpr uint32_t IDESC = tcx::IDESC_M128_N128_BF16;
 
 // LT = accumulator tiles per CTA.  LT=2: up to 5 positions per CTA pair (2+2 tiles), 4 weight stages of 32 KiB.
-//                                   LT=3: up to 7 positions per CTA pair (3+3 tiles), 3 weight stages.
-template <int LT>
+// X3 = split-bf16 numerics ("bf16x3", UTTT_EVAL_NET_BF16X3): activations and weights are kept as bf16 hi + lo pairs
+// (lo = bf16(x - hi)) and every K-block costs three MMAs, hi*hi + lo*hi + hi*lo, accumulated in fp32 in TMEM; the skip
+// connection is kept in fp32.  That is ~16 mantissa bits per operand: the mode that meets the reference's fp32 forward
+// (dual_network.py:89-121) within 1e-2 on random-init weights, at a third of the MMA rate.
+// Shared memory then holds 32 activation panels (16 hi + 16 lo) and a ring of 3 stages of 3 K-blocks (hi + lo = 8 KiB each).
+template <int LT, bool X3 = false>
 struct Cfg {
+    static_assert(LT == 2, "one instantiation: 2 tiles per CTA");
     static constexpr int LOC_TILES = LT;
     static constexpr int MAX_P = (LT == 2) ? 5 : 7;
     static constexpr int AROWS = (LEAD + 128 * LT + 11 + 7) / 8 * 8;
     static constexpr int PANEL_BYTES = AROWS * 16;
-    static constexpr int A_BYTES = 18 * PANEL_BYTES;      // 16 channel panels + the constant panel pair of the bias MMA
-    static constexpr int STAGES = (LT == 2) ? 4 : 3;
+    static constexpr int ACT_PANELS = X3 ? 32 : 16;        // channel panels [ci/8][row][8] bf16 (X3: panels 16.. hold the lo parts)
+    static constexpr int A_BYTES = (ACT_PANELS + 2) * PANEL_BYTES;      // + the constant panel pair of the bias MMA
+    static constexpr int STAGES = X3 ? 3 : ((LT == 2) ? 4 : 3);
+    // K-blocks (one K = 16 slice of a layer: 1 MMA per tile, X3: 3) per weight stage.  An issuer thread pays one barrier
+    // wait and one commit per stage (200+ cycles each while the tensor pipe saturates shared memory): with 4-block stages
+    // a CTA that owns ONE tile (batches of up to 148 positions) was issue-bound at ~93 cycles per MMA
+    static constexpr int STAGE_BLOCKS = X3 ? 3 : 8;
+    static constexpr int BLOCK_BYTES = X3 ? 8192 : 4096;   // [2 k-panels][128 co][8] bf16 (X3: hi block, then lo block)
+    static constexpr int STAGE_BYTES = STAGE_BLOCKS * BLOCK_BYTES;
+    static constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
+    static constexpr int IN_STAGES = X3 ? 3 : 2;           // conv_input: 9 taps x (K=16: 3 real channels); 16 tap slots (X3: 9)
+    static constexpr int GROUP_STAGES = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);   // every layer starts with its bias block
     // LT = 2 has TMEM for two accumulators per tile (4 x 128 = 512 columns): the layers alternate between them, and the
     // epilogue publishes its output per 16-column chunk (NQ act_ready barriers per tile), so the MMAs of layer L+1
     // run while the epilogue of layer L is still converting the other chunks.  (LT = 3 has one spare accumulator only;
@@ -65,7 +72,9 @@ struct Cfg {
     static constexpr int EPI_WARPS = 8 * LT;         // (tile, lane quarter, column half)
     static constexpr int THREADS = (EPI_WARPS + 1 + LT) * 32;
     static constexpr int SKIP_ROWS = 128 * LT;
+    static constexpr int SKIP_U4 = X3 ? 2 : 1;             // 16-byte units per (panel, row) of the skip buffer: 8 fp16 / 8 fp32
     static constexpr uint32_t TMEM_COLS = 512u;
+    static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
 using namespace tcx;
@@ -82,23 +91,26 @@ __host__ __device__ inline int group_positions(int n_pos, int n_pairs) {
 
 // the kernel body (a __device__ function so that net_auto.cu can put it behind a device-side dispatch together with
 // pp::trunk_pp_body); the __global__ wrappers are in net_tc2.cu
-template <int LT>
-__device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2][128][8] bf16
-                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [16 tap slots (9 used)][2][128][8] bf16
+template <int LT, bool X3 = false>
+__device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2][128][8] bf16 (X3: [32][72][hi, lo][2][128][8])
+                 const __nv_bfloat16* __restrict__ wq_in,// conv_input: [16 tap slots (9 used)][2][128][8] bf16 (X3: [9 taps][hi, lo][2][128][8])
                  const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
                  const __nv_bfloat16* __restrict__ planes,   // network input [rows][3][81] bf16
                  const float* __restrict__ headw,        // [3][128] policy conv (2) + value conv, BN scale folded; [384..386] shifts
                  float* headfeat,                        // out: [rows][243] = relu(policy conv)[2][81], relu(value conv)[81]
-                 uint4* skip,                            // [gridDim][16 panels][256 rows] fp16x8 skip connection
+                 uint4* skip,                            // [gridDim][16 panels][256 rows] fp16x8 skip connection (X3: fp32x8)
                  const int32_t* __restrict__ count,
                  int min_count, int max_count,           // this launch handles min_count < batch <= max_count
                  long long* dbg,
                  int n_pos_known = -1,                   // >= 0: the batch size (slot mode: counted from the slot flags, `count` unused)
                  const int* src_rows = nullptr) {        // slot mode: position i of this CTA pair reads planes row src_rows[i]
-    using C = Cfg<LT>;
+    using C = Cfg<LT, X3>;
     constexpr int LOC_TILES = C::LOC_TILES, MAX_P = C::MAX_P, PANEL_BYTES = C::PANEL_BYTES, A_BYTES = C::A_BYTES,
                   STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS,
-                  SKIP_ROWS = C::SKIP_ROWS, NQ = C::NQ;
+                  SKIP_ROWS = C::SKIP_ROWS, NQ = C::NQ, STAGE_BLOCKS = C::STAGE_BLOCKS, STAGE_BYTES = C::STAGE_BYTES,
+                  STAGES_PER_LAYER = C::STAGES_PER_LAYER, IN_STAGES = C::IN_STAGES, GROUP_STAGES = C::GROUP_STAGES,
+                  ACT_PANELS = C::ACT_PANELS, SKIP_U4 = C::SKIP_U4, BLOCK_BYTES = C::BLOCK_BYTES;
+    (void)MAX_P;
     extern __shared__ __align__(1024) uint8_t smem[];
     const long long t_entry = clock64();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -151,8 +163,9 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
     // constant panel 16: every row = (1, 1, 0, ..., 0).  One extra K=16 MMA per tile and layer multiplies it with the
     // layer's bias block (shift_hi, shift_lo in k = 0, 1), so the BatchNorm shift is added by the tensor pipe and the
     // epilogue has no bias loads or adds (measured: -20 % epilogue time).
+    // (X3: (1, 1, 1, 0, ...): the shift comes as three bf16 terms)
     for (int i = threadIdx.x; i < C::AROWS; i += THREADS)
-        reinterpret_cast<uint4*>(sA + (size_t)16 * PANEL_BYTES)[i] = make_uint4(0x3F803F80u, 0, 0, 0);
+        reinterpret_cast<uint4*>(sA + (size_t)ACT_PANELS * PANEL_BYTES)[i] = make_uint4(0x3F803F80u, X3 ? 0x00003F80u : 0u, 0, 0);
     fence_async_all();
     tc_fence_before();
     __syncthreads();
@@ -176,7 +189,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
             const bool valid = (pos < P) && (r < 9) && (c < 9) && (gpos < n_pos);
             float* hrow = headfeat + (size_t)gpos * 243 + (size_t)(r * 9 + c);
             float4* hscr = reinterpret_cast<float4*>(smem + C::HEAD_OFF) + lr;
-            uint4* srow_skip = skip + (size_t)blockIdx.x * (16 * SKIP_ROWS) + (size_t)(chalf * 8) * SKIP_ROWS + (size_t)lr;
+            uint4* srow_skip = skip + ((size_t)blockIdx.x * (16 * SKIP_ROWS) + (size_t)(chalf * 8) * SKIP_ROWS + (size_t)lr) * SKIP_U4;
             uint8_t* srow = sA + (size_t)(chalf * 8) * PANEL_BYTES + (size_t)(LEAD + lr) * 16;
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(lt * 128 + chalf * 64);
             const bool nb_lo = (quarter == 0) && (lt > 0);
@@ -240,10 +253,14 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                 // the skip connection (8 x 16 B per thread) is fetched from L2 while the MMAs still run
                 // (LT = 3 runs 896 threads at 72 registers: only the first half is prefetched there, the second half is
                 // fetched two chunks ahead of its use)
+                // (X3: fp32, 4 x 16 B per 16-column chunk; the chunks 0 and 1 are prefetched, 2 and 3 follow as 0 and 1 are used)
                 constexpr int SKP = (LT == 2) ? 8 : 4;
                 uint4 sk[SKP];
 #pragma unroll
-                for (int j = 0; j < SKP; j++) sk[j] = (second && valid) ? srow_skip[(size_t)j * SKIP_ROWS] : zero4;
+                for (int j = 0; j < SKP; j++) {
+                    if constexpr (X3) sk[j] = (second && valid) ? srow_skip[(size_t)(j >> 1) * SKIP_ROWS * 2 + (j & 1)] : zero4;
+                    else sk[j] = (second && valid) ? srow_skip[(size_t)j * SKIP_ROWS] : zero4;
+                }
                 mbar_wait_spin<false>(bar_accum + 8 * lt, lpar);
                 if (nb_lo) mbar_wait_spin<false>(bar_accum + 8 * (lt - 1), lpar);
                 if (nb_hi) mbar_wait_spin<false>(bar_accum + 8 * (lt + 1), lpar);
@@ -258,11 +275,21 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                     float* v = (ch & 1) ? vb : va;
                     tmem_ld_wait();
                     if (ch < 3) tmem_ld16(tsrc + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
-                    f16x8_add2(sk[(2 * ch) % SKP], v);
-                    f16x8_add2(sk[(2 * ch + 1) % SKP], v + 8);
-                    if (SKP == 4 && ch < 2 && second && valid) {     // refill the two registers just consumed: panels +4
-                        sk[(2 * ch) % SKP] = srow_skip[(size_t)(2 * ch + 4) * SKIP_ROWS];
-                        sk[(2 * ch + 1) % SKP] = srow_skip[(size_t)(2 * ch + 5) * SKIP_ROWS];
+                    if constexpr (X3) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) f32x4_add(sk[4 * (ch & 1) + j], v + 4 * j);
+                        if (ch < 2 && second && valid) {             // refill the four registers just consumed: chunk ch + 2
+#pragma unroll
+                            for (int j = 0; j < 4; j++)
+                                sk[4 * (ch & 1) + j] = srow_skip[(size_t)(2 * (ch + 2) + (j >> 1)) * SKIP_ROWS * 2 + (j & 1)];
+                        }
+                    } else {
+                        f16x8_add2(sk[(2 * ch) % SKP], v);
+                        f16x8_add2(sk[(2 * ch + 1) % SKP], v + 8);
+                        if (SKP == 4 && ch < 2 && second && valid) {     // refill the two registers just consumed: panels +4
+                            sk[(2 * ch) % SKP] = srow_skip[(size_t)(2 * ch + 4) * SKIP_ROWS];
+                            sk[(2 * ch + 1) % SKP] = srow_skip[(size_t)(2 * ch + 5) * SKIP_ROWS];
+                        }
                     }
                     if constexpr (last) {
                         // the trunk output never leaves the SM: policy_conv / value_conv (1x1, dual_network.py:102,111)
@@ -278,9 +305,27 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                     } else {
 #pragma unroll
                         for (int j = 0; j < 2; j++) {
-                            uint4 pk = valid ? relu_pack8_bf16(v + 8 * j) : zero4;      // padding rows stay zero
-                            *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = pk;
-                            if (keep && valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = relu_pack8_f16(v + 8 * j);
+                            if constexpr (X3) {
+                                // x = relu(v) = hi + lo (+ 2^-17 |x|): both halves feed the next layer's MMAs
+                                float x[8], l[8];
+#pragma unroll
+                                for (int i = 0; i < 8; i++) x[i] = fmaxf(v[8 * j + i], 0.0f);
+                                uint4 hi = pack8_bf16(x);
+                                bf16x8_residual(hi, x, l);
+                                uint4 lo = pack8_bf16(l);
+                                if (!valid) hi = lo = zero4;                             // padding rows stay zero
+                                *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = hi;
+                                *reinterpret_cast<uint4*>(srow + (size_t)(16 + ch * 2 + j) * PANEL_BYTES) = lo;
+                                if (keep && valid) {
+                                    uint4* d = srow_skip + (size_t)(ch * 2 + j) * SKIP_ROWS * 2;
+                                    d[0] = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+                                    d[1] = make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7]));
+                                }
+                            } else {
+                                uint4 pk = valid ? relu_pack8_bf16(v + 8 * j) : zero4;      // padding rows stay zero
+                                *reinterpret_cast<uint4*>(srow + (size_t)(ch * 2 + j) * PANEL_BYTES) = pk;
+                                if (keep && valid) srow_skip[(size_t)(ch * 2 + j) * SKIP_ROWS] = relu_pack8_f16(v + 8 * j);
+                            }
                         }
                         if (NQ == 4 || ch == 3) {        // channels 16(4*chalf + ch) .. +15 of these rows are in place
                             fence_async_smem();
@@ -288,8 +333,11 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                             __syncwarp();
                             if (lane == 0) {
                                 if (NQ == 4) {
-                                    publish(ch, 4 * HALO_BYTES);
-                                    if (bnd) { push_halo(2 * ch, ch); push_halo(2 * ch + 1, ch); }
+                                    publish(ch, (X3 ? 8 : 4) * HALO_BYTES);
+                                    if (bnd) {
+                                        push_halo(2 * ch, ch); push_halo(2 * ch + 1, ch);
+                                        if (X3) { push_halo(16 + 2 * ch, ch); push_halo(16 + 2 * ch + 1, ch); }
+                                    }
                                 } else {
                                     publish(0, 16 * HALO_BYTES);
                                     if (bnd) {
@@ -334,7 +382,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                     if (lane == 0) {
                         const __nv_bfloat16* src;
                         uint32_t bytes = STAGE_BYTES;
-                        if (st == 0) { src = wq_bias + (size_t)(layer + 1) * (BIAS_BYTES / 2); bytes = BIAS_BYTES; }
+                        if (st == 0) { src = wq_bias + (size_t)(layer + 1) * (BIAS_BYTES / 2); bytes = BIAS_BYTES; }   // (sizes in bf16 elements)
                         else if (layer < 0) src = wq_in + (size_t)(st - 1) * (STAGE_BYTES / 2);
                         else src = wq + (size_t)(layer * STAGES_PER_LAYER + st - 1) * (STAGE_BYTES / 2);
                         mbar_expect_tx(bar_full + 8 * stage, bytes);
@@ -355,7 +403,9 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
             const bool signal_peer = has_peer && (lt == bnd_tile);
             const uint64_t a_desc = make_desc(a_tile, PANEL_BYTES, 128);         // + (row shift + panel offset) / 16: shared
             const uint64_t b_desc = make_desc(sB_u, 2048, 128);                  //   addresses are < 256 KiB, no carry
-            const uint64_t bias_a = a_desc + (uint64_t)(16u * PANEL_BYTES / 16u);
+            const uint64_t bias_a = a_desc + (uint64_t)((uint32_t)ACT_PANELS * PANEL_BYTES / 16u);
+            constexpr uint64_t A_LO = (uint64_t)(16u * PANEL_BYTES / 16u);      // X3: descriptor offset of the lo panels
+            constexpr uint64_t B_BLK = (uint64_t)(BLOCK_BYTES / 16), B_LO = 256u; // per K-block / X3: of its lo half
             int gn = iter * GROUP_STAGES;
             int stage = gn % STAGES;
             uint32_t par = (uint32_t)((gn / STAGES) & 1);
@@ -402,9 +452,12 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
 #pragma unroll
                             for (int j = 0; j < STAGE_BLOCKS; j++) {
                                 const int tap = STAGE_BLOCKS * s + j;
-                                if (tap < 9)
-                                    umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)((tap / 3 - 1) * 10 + (tap % 3 - 1)),
-                                              b_st + (uint64_t)(j * 256), IDESC, 1u);
+                                if (tap < 9) {
+                                    const uint64_t a_tap = a_desc + (uint64_t)(int64_t)((tap / 3 - 1) * 10 + (tap % 3 - 1));
+                                    umma_bf16(tmem_d, a_tap, b_st + (uint64_t)j * B_BLK, IDESC, 1u);
+                                    // (the input planes are exact in bf16: no lo part on the A side)
+                                    if (X3) umma_bf16(tmem_d, a_tap, b_st + (uint64_t)j * B_BLK + B_LO, IDESC, 1u);
+                                }
                             }
                             release_stage();
                             if (s == IN_STAGES - 1) {
@@ -428,7 +481,14 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                                 if (q == 0 && dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[layer * 4 + 0] = clock64();
                             }
                             const int off = (tap / 3 - 1) * 10 + (tap % 3 - 1) + 2 * unit * (PANEL_BYTES / 16);
-                            if (leader) umma_bf16(tmem_d, a_desc + (uint64_t)(int64_t)off, b_st + (uint64_t)(ks * 256), IDESC, 1u);
+                            if (leader) {
+                                const uint64_t a_k = a_desc + (uint64_t)(int64_t)off, b_k = b_st + (uint64_t)ks * B_BLK;
+                                umma_bf16(tmem_d, a_k, b_k, IDESC, 1u);
+                                if (X3) {
+                                    umma_bf16(tmem_d, a_k + A_LO, b_k, IDESC, 1u);
+                                    umma_bf16(tmem_d, a_k, b_k + B_LO, IDESC, 1u);
+                                }
+                            }
                         }
                         if (leader) {
                             release_stage();

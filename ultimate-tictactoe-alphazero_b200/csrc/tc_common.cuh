@@ -224,6 +224,19 @@ __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
 __device__ __forceinline__ uint4 pack8_f16(const float* v) {
     return make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
 }
+// v[0..3] += 4 fp32 values
+__device__ __forceinline__ void f32x4_add(const uint4& q, float* v) {
+    v[0] += __uint_as_float(q.x); v[1] += __uint_as_float(q.y); v[2] += __uint_as_float(q.z); v[3] += __uint_as_float(q.w);
+}
+// l[i] = x[i] - float(hi[i]) for 8 packed bf16 (exact: the difference of a float and its bf16 rounding)
+__device__ __forceinline__ void bf16x8_residual(const uint4& hi, const float* x, float* l) {
+    const uint32_t w[4] = {hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        l[2 * i] = x[2 * i] - __uint_as_float(w[i] << 16);
+        l[2 * i + 1] = x[2 * i + 1] - __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+}
 // ReLU fused into the conversion (F2FP.RELU): max(x,0) then round to bf16 / fp16 (saturating)
 __device__ __forceinline__ uint32_t relu_bf16x2(float lo, float hi) {
     uint32_t d;

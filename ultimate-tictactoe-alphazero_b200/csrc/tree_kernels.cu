@@ -132,8 +132,7 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_begin_kernel(TreePa
     if (P.mode == MODE_SELFPLAY) {
         // the first games go to the slots in slot order (not in arrival order at an atomic counter: which game a slot
         // plays decides its row in the evaluator batch, and a run should be reproducible); later games are claimed from
-        // counters[0] as slots finish
-        if (t == 0 && lane == 0) atomicAdd(P.counters + 0, (unsigned long long)P.n_trees);
+        // counters[0] as slots finish (the host starts it at the number of slots before the lanes fork)
         unsigned long long g = (unsigned long long)(P.slot0 + t);
         if ((int64_t)g >= P.n_games) {
             c.phase = PHASE_DONE;

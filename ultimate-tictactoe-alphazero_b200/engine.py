@@ -12,7 +12,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libuttt_b200.so")
 
-EVAL_NET_BF16, EVAL_NET_FP32, EVAL_HASH, EVAL_HOST = 0, 1, 2, 3
+EVAL_NET_BF16, EVAL_NET_FP32, EVAL_HASH, EVAL_HOST, EVAL_NET_BF16X3 = 0, 1, 2, 3, 4
 SP_CORRECT_TERMINAL_SIGN = 1
 SP_THROUGHPUT = 2
 
@@ -79,6 +79,8 @@ ABI = {
     "uttt_debug_batch_histogram": ([_vp, _vp, C.c_int32], C.c_int),
     "uttt_last_run_profile": ([_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
     "uttt_set_profile_level": ([_vp, C.c_int], C.c_int),
+    "uttt_debug_trace": ([_vp, C.c_int], C.c_int),
+    "uttt_debug_trace_read": ([_vp, C.c_int64, C.POINTER(C.c_int64), _vp, _vp, _vp, _vp], C.c_int),
 }
 
 _lib = None
@@ -421,6 +423,23 @@ class Engine:
         out = np.zeros(64, np.int64)
         _check(self.lib.uttt_debug_batch_histogram(self.h, _ptr(out), 1 if reset else 0))
         return out
+
+    def trace(self, enable=True):
+        """start (and clear) / stop recording every evaluated leaf of the reference-exact search (diagnostics, slow)"""
+        _check(self.lib.uttt_debug_trace(self.h, 1 if enable else 0))
+
+    def trace_read(self):
+        """-> (meta (n,3) int32 [tree, game index, ply], states (n,8) uint32, policy (n,81) f32, value (n,) f32)"""
+        n = C.c_int64(0)
+        _check(self.lib.uttt_debug_trace_read(self.h, 0, C.byref(n), None, None, None, None))
+        n = n.value
+        meta = np.zeros((n, 3), np.int32)
+        st = np.zeros((n, 8), np.uint32)
+        pol = np.zeros((n, 81), np.float32)
+        val = np.zeros((n,), np.float32)
+        if n:
+            _check(self.lib.uttt_debug_trace_read(self.h, n, C.byref(n_ := C.c_int64(0)), _ptr(meta), _ptr(st), _ptr(pol), _ptr(val)))
+        return meta, st, pol, val
 
     def set_profile_level(self, level):
         """0: no per-kernel events during self-play, 1 (default): the trunk only, 2: tree / trunk / heads"""
