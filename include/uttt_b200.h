@@ -44,6 +44,12 @@ extern "C" {
                                            with Dirichlet noise, virtual loss, `batch_size` = leaves per tree per round
                                            (<= 16), single expansion per leaf, correct terminal sign (not in the reference) */
 
+#define UTTT_SP_PYSEARCH 4              /* uttt_mcts_search only: the semantics of the reference's pure-Python search
+                                           (pv_mcts.py:74-180, used by its gating match evaluate_network.py:73-75) instead
+                                           of the C++ one's: the root is evaluated like any leaf, a flush's k expansions
+                                           of a leaf replace each other (one child list), priors are normalised with
+                                           numpy's float32 pairwise sum */
+
 typedef struct uttt_engine uttt_engine;
 
 const char *uttt_last_error(void);
@@ -151,6 +157,11 @@ int uttt_mcts_search(uttt_engine *e, const uint32_t *roots, int32_t n_roots, int
  * (AlphaZero's settings; the reference has no noise).  eps = 0 disables it. */
 int uttt_set_root_noise(uttt_engine *e, float alpha, float eps);
 
+/* SP_TEMPERATURE of the self-play loop (self_play_cpp.py:27,62 -> cpp/uttt_mcts.cpp:183-216); default 1 (the reference's
+ * setting: moves drawn in proportion to the visit counts).  0: the first maximum of the visit counts is played; otherwise
+ * moves are drawn from n^(1/T) / sum.  The history always holds the raw visit counts. */
+int uttt_set_selfplay_temperature(uttt_engine *e, float temperature);
+
 /* step-wise form for a caller-side evaluator (python_bindings.cpp:11-47 `wrap_python_inference`) */
 int uttt_mcts_begin(uttt_engine *e, const uint32_t *roots, int32_t n_roots, int32_t evaluate_count,
                     int32_t batch_size);
@@ -182,6 +193,12 @@ int uttt_selfplay_run(uttt_engine *e, int64_t n_games, uint64_t game0, int32_t e
                       int32_t batch_size, uint32_t seed, int32_t evaluator, int32_t flags,
                       uint32_t *hist_states, uint16_t *hist_counts, uint8_t *hist_actions,
                       int32_t *hist_len, int8_t *hist_final, int64_t *stats);
+
+/* progress of a running uttt_selfplay_run*: `fn(finished games, n_games, user)` is called on the calling thread whenever the
+ * host sees the count of finished games change (once per window of 8 rounds) -- what the reference prints per game
+ * (self_play_cpp.py:121).  NULL removes it. */
+typedef void (*uttt_progress_fn)(int64_t done, int64_t total, void *user);
+int uttt_set_progress_callback(uttt_engine *e, uttt_progress_fn fn, void *user);
 
 /* device-resident variant for benchmarking / multi-GPU pipelines: runs the same loop but leaves
  * the history in the engine's HBM buffers; uttt_selfplay_fetch copies it out afterwards. */

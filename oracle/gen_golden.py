@@ -189,12 +189,86 @@ def gen_network():
     print("network.npz:", len(states), "positions; params", sum(t.numel() for t in model.parameters()))
 
 
+def gen_pymcts():
+    """Scores of the REFERENCE's pure-Python search -- /root/reference/pv_mcts.py:74-180, the one its gating match uses
+    (evaluate_network.py:73-75) -- imported and run unmodified under the integer-hash evaluator.  `model` is a stand-in
+    whose forward returns the hash policy / value of the states the reference code is about to evaluate (recorded by
+    wrapping pv_mcts.state_to_input_tensor, which predict_batch calls once per state, pv_mcts.py:24); everything else --
+    predict_batch's legal-move renormalisation with np.sum, the tree, PUCT, the queue / flush loop, boltzman -- is the
+    reference's own code under this container's NumPy (the version is stored with the vectors)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))      # the reference's own pybind module (self_play_cpp imports it)
+    sys.path.insert(0, "/root/reference")
+    import pv_mcts as ref_pv                                       # noqa: E402  (prints the device line)
+    import game as ref_game
+    seen = []
+    real_tensor = ref_pv.state_to_input_tensor
+
+    def recording_tensor(state):
+        seen.append(state)
+        return real_tensor(state)
+    ref_pv.state_to_input_tensor = recording_tensor
+
+    class HashModel:
+        def eval(self):
+            return self
+
+        def __call__(self, x):
+            n = x.shape[0]
+            states = seen[-n:]
+            pol = np.zeros((n, 81), np.float32)
+            val = np.zeros((n, 1), np.float32)
+            for i, st in enumerate(states):
+                o = O.OrcState()
+                for b_ in range(9):
+                    for c_ in range(9):
+                        o.pieces[9 * b_ + c_] = st.pieces[b_][c_]
+                        o.enemy[9 * b_ + c_] = st.enemy_pieces[b_][c_]
+                    o.main_pieces[b_] = st.main_board_pieces[b_]
+                    o.main_enemy[b_] = st.main_board_enemy_pieces[b_]
+                o.active = st.active_board
+                v = C.c_float()
+                O.oracle().orc_hash_eval(C.byref(o), pol[i], C.byref(v))
+                val[i, 0] = v.value
+            del seen[:]
+            return torch.from_numpy(pol), torch.from_numpy(val)
+
+    def py_state(w):
+        o = O.state_from_packed(w)
+        return ref_game.State([[o.pieces[9 * b_ + c_] for c_ in range(9)] for b_ in range(9)],
+                              [[o.enemy[9 * b_ + c_] for c_ in range(9)] for b_ in range(9)],
+                              list(o.main_pieces), list(o.main_enemy), o.active)
+    states = np.concatenate([O.playout_states(SEED + 4, g)[0][:-1:5] for g in range(20)])
+    model = HashModel()
+    cases, scores = [], []
+    for si, w in enumerate(states):
+        for sims, batch in ((50, 8), (50, 1), (10, 2), (37, 5), (200, 8)):
+            if sims == 200 and si % 4:
+                continue
+            ref_pv.PV_EVALUATE_COUNT, ref_pv.MCTS_BATCH_SIZE = sims, batch
+            for T in (1.0, 0.0, 0.5):
+                if T == 0.5 and si % 3:
+                    continue
+                sc = np.asarray(ref_pv.pv_mcts_scores(model, py_state(w), T), dtype=np.float64)
+                row = np.zeros(81, np.float64)
+                row[:len(sc)] = sc
+                cases.append((si, sims, batch, T, len(sc)))
+                scores.append(row)
+    np.savez_compressed(os.path.join(OUT, "pymcts.npz"), states=states, cases=np.array(cases, np.float64),
+                        scores=np.stack(scores).view(np.uint64), numpy_version=np.array(np.__version__))
+    print("pymcts.npz:", len(states), "states,", len(cases), "cases (numpy %s)" % np.__version__)
+
+
 if __name__ == "__main__":
     if not O.ref_available():
         sys.exit("oracle/_ref is not built: run `make -C oracle ref` where /root/reference exists")
     os.makedirs(OUT, exist_ok=True)
+    if "--pymcts-only" in sys.argv:
+        gen_pymcts()
+        sys.exit(0)
     gen_rules()
     gen_mcts()
     gen_selfplay()
     gen_boltzman()
     gen_network()
+    gen_pymcts()

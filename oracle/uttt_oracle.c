@@ -443,6 +443,99 @@ int orc_pv_mcts_scores_hash(const orc_state *root, float temperature, int evalua
                               scores_out, counts_out, stats_out);
 }
 
+/* ------------------------------------------------ the reference's pure-Python search (pv_mcts.py:74-180)
+ * Used by its gating match (evaluate_network.py:73-75).  Same PUCT / backup arithmetic as the C++ search (float32
+ * throughout under NumPy >= 2 scalar promotion: the network outputs are np.float32, Python ints / floats are weak), but
+ *   - the root starts unexpanded and is evaluated like any leaf (pv_mcts.py:133,142),
+ *   - expand() REPLACES the child list (pv_mcts.py:105-109): the k queued copies of a leaf leave ONE list,
+ *   - priors: policy[legal] / np.sum(policy[legal]) with numpy's float32 pairwise summation (pv_mcts.py:45-49),
+ *   - scores: visit counts, turned into float64 probabilities by the caller (pv_mcts.py:166-180).
+ * The loop is kept literal (queue, flush rule pv_mcts.py:154-165). */
+static float numpy_sum_f32(const float *a, int n) {
+    if (n < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < n; i++) res += a[i];
+        return res;
+    }
+    float r[8];
+    for (int j = 0; j < 8; j++) r[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; j++) r[j] += a[i + j];
+    float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+}
+
+static void expand_replace(orc_node *nd, const float *policies, int npol) {      /* pv_mcts.py:105-109 */
+    for (int i = 0; i < nd->n_child; i++) node_free(nd->child[i]);
+    nd->n_child = 0;
+    expand(nd, policies, npol);
+}
+
+int orc_py_mcts_counts(orc_eval_fn eval, void *ctx, const orc_state *root_state, int evaluate_count, int batch_size,
+                       int *counts_out) {
+    int root_legal[81];
+    int nroot = orc_legal_actions(root_state, root_legal);
+    if (nroot == 0 || orc_is_lose(root_state)) return 0;
+    orc_node *root = node_new(root_state, 0.0f);                          /* pv_mcts.py:133 */
+    int qcap = batch_size > 0 ? batch_size : 1;
+    orc_node **q_leaf = (orc_node **)malloc(sizeof(orc_node *) * (size_t)qcap);
+    orc_node **q_path = (orc_node **)malloc(sizeof(orc_node *) * (size_t)qcap * ORC_MAX_PATH);
+    int *q_plen = (int *)malloc(sizeof(int) * (size_t)qcap);
+    orc_state *bstates = (orc_state *)malloc(sizeof(orc_state) * (size_t)qcap);
+    float *bpol = (float *)malloc(sizeof(float) * 81 * (size_t)qcap);
+    float *bval = (float *)malloc(sizeof(float) * (size_t)qcap);
+    int nq = 0;
+    for (int i = 0; i < evaluate_count; i++) {                            /* pv_mcts.py:139 */
+        orc_node *path[ORC_MAX_PATH];
+        int plen = 0;
+        float value;
+        orc_node *leaf = search_leaf(root, path, &plen, &value);          /* :142 (same descent and terminal sign) */
+        if (orc_is_done(&leaf->state)) {                                  /* :145-147 */
+            backpropagate(path, plen, value);
+            continue;
+        }
+        if (leaf->n == 0) {                                               /* :150-152 */
+            q_leaf[nq] = leaf;
+            memcpy(q_path + (size_t)nq * ORC_MAX_PATH, path, sizeof(orc_node *) * (size_t)plen);
+            q_plen[nq] = plen;
+            nq++;
+        }
+        if (nq >= batch_size || i == evaluate_count - 1) {                /* :157 */
+            if (nq > 0) {
+                for (int j = 0; j < nq; j++) bstates[j] = q_leaf[j]->state;
+                eval(ctx, bstates, nq, bpol, bval);                       /* :160-161 predict_batch */
+                for (int j = 0; j < nq; j++) {
+                    orc_node *lf = q_leaf[j];
+                    int legal[81];
+                    int nl = orc_legal_actions(&lf->state, legal);
+                    float lp[81];
+                    for (int k = 0; k < nl; k++) lp[k] = bpol[81 * j + legal[k]];
+                    float sum = numpy_sum_f32(lp, nl);                    /* :47 */
+                    if (sum > 0) {
+                        for (int k = 0; k < nl; k++) lp[k] /= sum;        /* :49 */
+                    } else {
+                        for (int k = 0; k < nl; k++) lp[k] = 1.0f / (float)nl;    /* :54 (float64 there; unreachable) */
+                    }
+                    expand_replace(lf, lp, nl);                           /* :164 */
+                    backpropagate(q_path + (size_t)j * ORC_MAX_PATH, q_plen[j], bval[j]);   /* :165 */
+                }
+                nq = 0;
+            }
+        }
+    }
+    int nchild = root->n_child;
+    for (int i = 0; i < nchild; i++) counts_out[i] = root->child[i]->n;
+    node_free(root);
+    free(q_leaf); free(q_path); free(q_plen); free(bstates); free(bpol); free(bval);
+    return nchild;
+}
+
+int orc_py_mcts_counts_hash(const orc_state *root, int evaluate_count, int batch_size, int *counts_out) {
+    return orc_py_mcts_counts(hash_eval_cb, NULL, root, evaluate_count, batch_size, counts_out);
+}
+
 /* Replay evaluator: the search is fed recorded (leaf state -> policy, value) rows, e.g. the rows a GPU engine's network
  * produced for exactly these leaves (tests/test_gpu_replay.py: "identical network outputs on both sides").  Entries are
  * consumed in order; the k queued copies of one leaf inside a batch (cpp/uttt_mcts.cpp:121-127) share one entry. */

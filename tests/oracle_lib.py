@@ -73,6 +73,8 @@ def oracle():
         L.orc_pv_mcts_scores_hash_record.argtypes = [SP, C.c_float, C.c_int, C.c_int, C.c_int, u32p, f32p, f32p,
                                                      C.POINTER(C.c_int), f32p]
         L.orc_pv_mcts_scores_hash_record.restype = C.c_int
+        L.orc_py_mcts_counts_hash.argtypes = [SP, C.c_int, C.c_int, i32p]
+        L.orc_py_mcts_counts_hash.restype = C.c_int
         L.orc_az_search_hash.argtypes = [SP, C.c_int, i32p]
         L.orc_az_search_hash.restype = C.c_int
         _oracle = L
@@ -201,6 +203,14 @@ def record_hash_mcts(w, temperature, sims, batch, cap=4096):
     m = oracle().orc_pv_mcts_scores_hash_record(C.byref(s), temperature, sims, batch, cap, st, pol, val, C.byref(n), sc)
     assert n.value <= cap
     return sc[:m].copy(), st[:n.value], pol[:n.value], val[:n.value]
+
+
+def oracle_py_mcts(w, sims, batch):
+    """root visit counts of the reference's pure-Python search (pv_mcts.py:74-180) under the hash evaluator"""
+    s = state_from_packed(w)
+    cn = np.zeros(81, np.int32)
+    n = oracle().orc_py_mcts_counts_hash(C.byref(s), sims, batch, cn)
+    return cn[:n].copy()
 
 
 def oracle_az_search(w, sims):

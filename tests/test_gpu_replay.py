@@ -82,12 +82,16 @@ def test_slot_mode_search_replays_bit_exactly_in_every_band(nets, n_roots):
         hist = e.batch_histogram()
         assert hist[(n_roots - 1) >> 4] + hist[min(63, n_roots >> 4)] > 0, hist      # the band did occur
         if n_roots > 370:
-            # the one-tile group of the 371..518 band accumulates split K (other bits than a stand-alone forward): those
-            # rows are checked on a well-conditioned network, where a re-association stays far below a wrong row
+            # the one-tile group of the 371..518 band accumulates split K (other bits than a stand-alone forward; a
+            # different fp32 sum can round an activation to the neighbouring bf16 value, so two bf16 evaluations of one
+            # position differ by up to the bf16 error itself, ~1e-2 in the value): those rows are checked on a
+            # well-conditioned network, where that noise stays far below the difference between two positions
             assert same.mean() > 0.5
             e.upload_model(damped)
             same, p2, pol, v2, val = _search_and_replay(e, roots, 50, 8, engine.EVAL_NET_BF16, exact_rows=False)
-            assert np.abs(p2 - pol).max() < 1e-3 and np.abs(v2 - val).max() < 1e-3
+            assert same.mean() > 0.5 and np.abs(p2 - pol).max() < 1e-3 and np.abs(v2 - val).max() < 3e-2
+            wrong = np.roll(np.arange(len(val)), 1)                # what a row handed to the wrong tree would look like
+            assert np.median(np.abs(p2[wrong] - pol).max(1)) > 1e-3
         # other search shapes of the same path
         for sims, batch, T in ((50, 1, 1.0), (37, 5, 0.0), (10, 2, 1.0)):
             _search_and_replay(e, roots[: min(n_roots, 96)], sims, batch, engine.EVAL_NET_BF16, exact_rows=False, temperature=T)

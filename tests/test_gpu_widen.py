@@ -11,6 +11,8 @@ def _sequential_match(models, n_games, seed, temperature):
     """evaluate_network.py:33-54,78-85 restated with one search per move through the single-position API"""
     import uttt_cpp
     import pv_mcts_cpp
+    import evaluate_network as en
+    assert uttt_cpp.NUMERICS == en.EN_NUMERICS
     points = []
     for i in range(n_games):
         rng = np.random.RandomState([seed & 0x7FFFFFFF, i])
@@ -26,19 +28,74 @@ def _sequential_match(models, n_games, seed, temperature):
     return points
 
 
-def test_gating_match_batched_equals_sequential():
+def test_gating_search_matches_the_reference_python_search(golden_dir):
+    """the gating match's search (evaluate_network.py:73-75 -> pv_mcts.py:74-180) on the engine (UTTT_SP_PYSEARCH) ==
+    the scores of the UNMODIFIED reference module under the hash evaluator (tests/golden/pymcts.npz), float64 bit for bit;
+    and == the C restatement on positions the goldens do not hold"""
+    import engine
+    import evaluate_network as en
+    import oracle_lib as O
+    with np.load(os.path.join(golden_dir, "pymcts.npz")) as z:
+        states, cases, scores = z["states"], z["cases"], z["scores"].view(np.float64)
+    e = engine.Engine(n_slots=len(states), max_sims=200, max_batch=8, max_games=1)
+    try:
+        checked = 0
+        for sims, batch in sorted({(int(c[1]), int(c[2])) for c in cases}):
+            _, counts, ns = e.mcts_search(states, sims, batch, 1.0, engine.EVAL_HASH, flags=engine.SP_PYSEARCH)
+            for (si, s_, b_, T, n), want in zip(cases, scores):
+                if (int(s_), int(b_)) != (sims, batch):
+                    continue
+                si, n = int(si), int(n)
+                assert ns[si] == n
+                got = en.python_scores(counts[si, :n], T)
+                assert got.tobytes() == want[:n].tobytes(), (si, sims, batch, T)
+                checked += 1
+        assert checked == len(cases) > 2000
+        more = np.concatenate([O.playout_states(777, g)[0][:-1] for g in range(12)])[:512]
+        e2 = engine.Engine(n_slots=512, max_sims=50, max_batch=8, max_games=1)
+        try:
+            _, counts, ns = e2.mcts_search(more, 50, 8, 1.0, engine.EVAL_HASH, flags=engine.SP_PYSEARCH)
+            for i, w in enumerate(more):
+                want = O.oracle_py_mcts(w, 50, 8)
+                assert ns[i] == len(want) and (counts[i, :ns[i]] == want).all(), i
+        finally:
+            e2.close()
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("search", ["python", "cpp"])
+def test_gating_match_batched_equals_sequential(search):
+    """all games of a match advance together (one batched search per ply and network); move for move the same match as
+    the reference's one-game-at-a-time loop (evaluate_network.py:33-54,78-85) with one search per move"""
     import torch
+    import engine
     import evaluate_network as en
     from dual_network import DualNetwork
     torch.manual_seed(1); m0 = DualNetwork().eval()
     torch.manual_seed(2); m1 = DualNetwork().eval()
-    actors = (en.NetworkActor(m0, 1.0, 6), en.NetworkActor(m1, 1.0, 6))
+    actors = (en.NetworkActor(m0, 1.0, 6, search=search), en.NetworkActor(m1, 1.0, 6, search=search))
     try:
         pts = en.play_matches(actors, 6, seed=77)
+        if search == "cpp":
+            assert pts == _sequential_match((m0, m1), 6, 77, 1.0)
+        else:
+            import uttt_cpp
+            want = []
+            for i in range(6):
+                rng = np.random.RandomState([77, i])
+                order = actors if i % 2 == 0 else tuple(reversed(actors))
+                state = uttt_cpp.State()
+                while not state.is_done():
+                    actor = order[0] if state.is_first_player() else order[1]
+                    sc, ns = actor.scores(state.packed().reshape(1, 8))
+                    state = state.next(int(rng.choice(state.legal_actions(), p=sc[0, :ns[0]])))
+                fp = (0 if state.is_first_player() else 1) if state.is_lose() else 0.5
+                want.append(fp if i % 2 == 0 else 1 - fp)
+            assert pts == want
     finally:
         for a in actors:
             a.close()
-    assert pts == _sequential_match((m0, m1), 6, 77, 1.0)
     assert all(p in (0, 0.5, 1) for p in pts)
 
 

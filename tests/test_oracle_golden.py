@@ -153,3 +153,32 @@ def test_replay_evaluator_reproduces_the_hash_search():
                     got, _, _ = O.table_mcts(w, T, sims, batch, st, np.roll(pol, 1, axis=0), np.roll(val, 1))
                     detected.append(got.tobytes() != want.tobytes())
     assert len(detected) > 20 and np.mean(detected) > 0.8, (len(detected), np.mean(detected))
+
+
+def _py_scores(counts, T):
+    """pv_mcts.py:166-180 on root visit counts (float64 python arithmetic)"""
+    if T == 0:
+        out = np.zeros(len(counts))
+        out[int(np.argmax(counts))] = 1
+        return out
+    xs = [int(x) ** (1 / T) for x in counts]
+    return np.array([x / sum(xs) for x in xs])
+
+
+def test_python_search_oracle_matches_reference_goldens(golden_dir):
+    """oracle restatement of the reference's pure-Python search (pv_mcts.py:74-180, the gating match's search) ==
+    the scores of the unmodified reference module (tests/golden/pymcts.npz, minted by oracle/gen_golden.py)"""
+    import os
+    with np.load(os.path.join(golden_dir, "pymcts.npz")) as z:
+        states, cases, scores = z["states"], z["cases"], z["scores"].view(np.float64)
+    assert len(cases) > 2000
+    differs_from_cpp = 0
+    for (si, sims, batch, T, n), want in zip(cases, scores):
+        si, sims, batch, n = int(si), int(sims), int(batch), int(n)
+        cn = O.oracle_py_mcts(states[si], sims, batch)
+        assert len(cn) == n and cn.sum() <= sims
+        got = _py_scores(cn, T)
+        assert got.tobytes() == want[:n].tobytes(), (si, sims, batch, T)
+        if T == 1.0 and sims == 50 and batch == 8:
+            differs_from_cpp += int((O.oracle_mcts(states[si], 1.0, sims, batch)[1] != cn).any())
+    assert differs_from_cpp > 50          # the two searches of the reference really are different algorithms

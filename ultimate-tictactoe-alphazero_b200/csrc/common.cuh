@@ -69,6 +69,7 @@ struct TreeParams {
     int32_t* tp_paths;        // [n_trees][TP_MAX_LEAVES][PATH_CAP]
     int32_t* tp_aux;          // [n_trees][2][TP_MAX_LEAVES]: path lengths, evaluator rows
     float dir_alpha, dir_eps; // Dirichlet root noise
+    float temperature;        // self-play move sampling (SP_TEMPERATURE, self_play_cpp.py:27); 1 = the reference's setting
     TreeCtl* ctl;             // [n_trees]
     int32_t* path;            // [n_trees][PATH_CAP]
     // nodes, [n_trees][node_cap], 16 B each: {n:16 | action<<16, w, p, first_child:20 | n_children<<20}

@@ -104,6 +104,8 @@ struct uttt_engine {
     std::vector<void*> allocs;
     // diagnostics (uttt_debug_trace): every evaluated leaf of the reference-exact search with the rows its tree is about to
     // consume -- what tests/test_gpu_replay.py feeds to the CPU reference search
+    uttt_progress_fn progress_cb;     // self-play: called when the number of finished games changed (per window of rounds)
+    void* progress_user;
     bool trace_on;
     struct TraceRec { int32_t tree, game_idx, ply; float value; uint32_t state[8]; float policy[81]; };
     std::vector<TraceRec> trace;
@@ -286,6 +288,8 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     memset(&e->w, 0, sizeof(e->w));
     e->cfg = *cfg;
     e->trace_on = false;
+    e->progress_cb = nullptr;
+    e->progress_user = nullptr;
     e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 4;
     e->prof_level = getenv("UTTT_PROFILE") ? atoi(getenv("UTTT_PROFILE")) : 1;
     e->lane_threshold = getenv("UTTT_LANE_THRESHOLD") ? atoi(getenv("UTTT_LANE_THRESHOLD")) : 1024;
@@ -316,6 +320,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         return 1;
     }
     UTTT_CUDA_OK(cudaMemset(t.ctl, 0, S * sizeof(TreeCtl)));
+    UTTT_CUDA_OK(cudaMemset(e->tc_dbg, 0, (128 + 64 + 8 + 16) * sizeof(long long)));
     UTTT_CUDA_OK(cudaMemset(t.nn_count, 0, 2 * N_LANES * sizeof(int32_t)));
     for (int i = 0; i < N_LANES; i++) {
         UTTT_CUDA_OK(cudaStreamCreateWithFlags(&e->lane_stream[i], cudaStreamNonBlocking));
@@ -336,6 +341,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     t.max_terminal = getenv("UTTT_MAX_TERMINAL") ? atoi(getenv("UTTT_MAX_TERMINAL")) : 4;   // measured on the 500-game cycle: 2..4 best, 8: +0.8 %, 50: +8 %
     t.dir_alpha = 0.3f;
     t.dir_eps = 0.25f;
+    t.temperature = 1.0f;
     *out = e;
     return 0;
 }
@@ -589,11 +595,11 @@ int uttt_net_forward(uttt_engine* e, const uint32_t* states_dev, int64_t n, int 
 }
 
 // ---------------------------------------------------------------------------- search
-int uttt_mcts_begin(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int32_t sims, int32_t batch) {
+static int mcts_begin_impl(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int32_t sims, int32_t batch, int32_t flags) {
     if (check_search_args(e, n_roots, sims, batch)) return 1;
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     TreeParams& t = e->tp;
-    t.n_trees = n_roots; t.sims = sims; t.batch = batch; t.mode = MODE_SEARCH; t.flags = 0;
+    t.n_trees = n_roots; t.sims = sims; t.batch = batch; t.mode = MODE_SEARCH; t.flags = flags;
     t.parity = 0; t.row_stride = 1; t.copy_stride = 0; t.slot_flags = nullptr;
     e->s_n_roots = n_roots; e->s_sims = sims; e->s_batch = batch; e->s_round = 0; e->s_pending = 0;
     e->s_per_copy = 0; e->s_have_results = 0;
@@ -602,6 +608,10 @@ int uttt_mcts_begin(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int3
     UTTT_CUDA_OK(cudaMemsetAsync(t.counters, 0, 8 * sizeof(unsigned long long), e->stream));
     UTTT_CUDA_OK(launch_tree_begin(t, e->stream));
     return 0;
+}
+
+int uttt_mcts_begin(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int32_t sims, int32_t batch) {
+    return mcts_begin_impl(e, roots, n_roots, sims, batch, 0);
 }
 
 int uttt_mcts_advance(uttt_engine* e, int32_t* n_pending) {
@@ -672,10 +682,10 @@ int uttt_mcts_search(uttt_engine* e, const uint32_t* roots, int32_t n_roots, int
                "uttt_mcts_search needs a device evaluator; use the step-wise calls for UTTT_EVAL_HOST");
     const bool tp = (flags & UTTT_SP_THROUGHPUT) != 0;
     UTTT_CHECK(!tp || batch <= TP_MAX_LEAVES, "throughput mode: at most %d leaves per tree per round", TP_MAX_LEAVES);
-    if (uttt_mcts_begin(e, roots, n_roots, sims, batch)) return 1;     // uploads roots, runs the compat begin kernel
+    UTTT_CHECK(!(tp && (flags & UTTT_SP_PYSEARCH)), "UTTT_SP_PYSEARCH and UTTT_SP_THROUGHPUT exclude each other");
+    if (mcts_begin_impl(e, roots, n_roots, sims, batch, flags)) return 1;     // uploads roots, runs the compat begin kernel
     if (n_roots == 0) return 0;
     TreeParams& t = e->tp;
-    t.flags = flags;
     if (tp) UTTT_CUDA_OK(launch_tree_tp_begin(t, e->stream));
     // rounds are enqueued without host synchronisation; the tree kernel ignores finished trees.
     // Upper bound on rounds: every round retires >= 1 simulation of every unfinished tree (+ root evaluation).
@@ -722,6 +732,19 @@ int uttt_set_root_noise(uttt_engine* e, float alpha, float eps) {
     return 0;
 }
 
+int uttt_set_progress_callback(uttt_engine* e, uttt_progress_fn fn, void* user) {
+    UTTT_CHECK(e != nullptr, "null engine");
+    e->progress_cb = fn;
+    e->progress_user = user;
+    return 0;
+}
+
+int uttt_set_selfplay_temperature(uttt_engine* e, float temperature) {
+    UTTT_CHECK(e && temperature >= 0.0f && temperature == temperature, "bad temperature");
+    e->tp.temperature = temperature;
+    return 0;
+}
+
 int uttt_boltzman(const float* xs, int32_t n, float temperature, float* out) {
     UTTT_CHECK(xs && out && n >= 0, "bad argument");
     UTTT_CHECK(temperature != 0.0f, "temperature must be non-zero");
@@ -748,6 +771,7 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
                "self-play needs a device evaluator");
     int n_trees = (int)((n_games < e->cfg.n_slots) ? n_games : e->cfg.n_slots);
     if (check_search_args(e, n_trees, sims, batch)) return 1;
+    UTTT_CHECK(!(flags & UTTT_SP_PYSEARCH), "UTTT_SP_PYSEARCH is a search option (uttt_mcts_search), not a self-play mode");
     const bool tp = (flags & UTTT_SP_THROUGHPUT) != 0;
     UTTT_CHECK(!tp || batch <= TP_MAX_LEAVES, "throughput mode: at most %d leaves per tree per round", TP_MAX_LEAVES);
     const int rows_per_tree = tp ? batch : 1;
@@ -808,7 +832,7 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     // every round retires >= 1 simulation of every live slot: hard upper bound on rounds
     int64_t waves = (n_games + n_trees - 1) / n_trees;
     int64_t max_rounds = waves * 82 * (int64_t)(sims + 3) * (tp ? 4 : 1) + CHECK_EVERY;
-    int64_t r = 0;
+    int64_t r = 0, reported = 0;
     bool done = false;
     // Two windows of CHECK_EVERY rounds are kept in flight: window w+1 is enqueued before the host waits for window w,
     // so the GPU never idles while the host reads the progress counters and the per-kernel event times (one window at
@@ -853,6 +877,10 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
         UTTT_CHECK(hc[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
         // lane 0's copy may predate lane 1's last rounds: "done" only ever lags, never leads
         done = (int64_t)hc[1] >= n_games;
+        if (e->progress_cb && (int64_t)hc[1] != reported) {
+            reported = (int64_t)hc[1];
+            e->progress_cb(reported < n_games ? reported : n_games, n_games, e->progress_user);
+        }
         return 0;
     };
     int head = 0, in_flight = 0;                 // windows are retired in the order they were enqueued

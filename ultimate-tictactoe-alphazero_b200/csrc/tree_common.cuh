@@ -67,7 +67,60 @@ __device__ __forceinline__ void warp_write_planes(__nv_bfloat16* pl, const Packe
 }
 
 // Philox temperature-1 sampling over the root visit counts; returns the chosen action.
+// SP_TEMPERATURE != 1 (self_play_cpp.py:27,62 -> cpp/uttt_mcts.cpp:183-216): T == 0 plays the first maximum of the visit
+// counts (the reference's one-hot scores leave np.random.choice no choice); otherwise the move is drawn from
+// n_i^(1/T) / sum with the same Philox draw as the T == 1 sampler (fp32 weights, a fixed-order warp scan)
+__device__ __forceinline__ int sample_move_temperature(const TreeParams& P, const TreeView& T, const TreeCtl& c, const uint32_t lm[3],
+                                                       int lane) {
+    const int L = c.n_root;
+    if (P.temperature == 0.0f) {
+        int best = -1, besti = 0x7FFFFFFF;
+        for (int i = lane; i < L; i += 32) {
+            int n = node_n(T.node[1 + i]);
+            if (n > best) { best = n; besti = i; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            int ob = __shfl_xor_sync(FULL, best, off), oi = __shfl_xor_sync(FULL, besti, off);
+            if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+        }
+        return nth_legal(lm, besti);
+    }
+    const float inv = __fdiv_rn(1.0f, P.temperature);
+    Philox4 r = philox4x32(P.seed, 1u, (uint32_t)c.game, (uint32_t)(c.game >> 32), (uint32_t)c.ply, 0u);
+    const float u = (float)(r.x >> 8) * (1.0f / 16777216.0f);          // [0, 1)
+    // pass 1: total weight (same scan as pass 2, so the threshold u * total is consistent with the prefix sums)
+    float total = 0.0f;
+    for (int pass = 0; pass < 2; pass++) {
+        float carry = 0.0f;
+        const float thr = __fmul_rn(u, total);
+        for (int base = 0; base < L; base += 32) {
+            const int i = base + lane;
+            float incl = (i < L) ? powf((float)node_n(T.node[1 + i]), inv) : 0.0f;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                float o = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl = __fadd_rn(incl, o);
+            }
+            incl = __fadd_rn(incl, carry);
+            if (pass == 1) {
+                unsigned hit = __ballot_sync(FULL, (i < L) && (incl > thr));
+                if (hit) return nth_legal(lm, base + (__ffs((int)hit) - 1));
+            }
+            carry = __shfl_sync(FULL, incl, 31);
+        }
+        total = carry;
+    }
+    // rounding left u * total >= every prefix sum: the last visited child
+    int last = 0;
+    for (int i = lane; i < L; i += 32)
+        if (node_n(T.node[1 + i]) > 0) last = i;
+    last = __reduce_max_sync(FULL, last);
+    return nth_legal(lm, last);
+}
+
 __device__ __forceinline__ int sample_move(const TreeParams& P, const TreeView& T, const TreeCtl& c, const uint32_t lm[3], int lane) {
+    if (P.temperature != 1.0f) return sample_move_temperature(P, T, c, lm, lane);
     int L = c.n_root;
     int tot = 0;
     for (int i = lane; i < L; i += 32) tot += node_n(T.node[1 + i]);

@@ -33,6 +33,16 @@ namespace uttt {
 __device__ void init_root(const TreeParams& P, const TreeView& T, TreeCtl& c, const PackedState& rs, int lane) {
     uint32_t lm[3];
     int L = legal_mask(rs, lm);
+    if (P.flags & UTTT_SP_PYSEARCH) {
+        // pv_mcts.py:133: the root starts as an unexpanded leaf; the first simulations queue the root itself
+        if (lane == 0) T.node[0] = make_uint4(0x7Fu << 16, 0u, 0u, 0u);
+        c.n_nodes = 1;
+        c.n_root = L;
+        c.sims_left = P.sims;
+        c.path_len = 0;
+        c.pend_k = 0;
+        return;
+    }
     float pu = (L > 0) ? __fdiv_rn(1.0f, (float)L) : 0.0f;
     if (lane == 0) T.node[0] = make_uint4(0x7Fu << 16, 0u, 0u, (L > 0 ? 1u : 0u) | ((uint32_t)L << 20));
     for (int a = lane; a < 81; a += 32)
@@ -69,6 +79,73 @@ __device__ void backup(const TreeView& T, int plen, int k, const float* vals, in
         *nw = q;
     }
     __syncwarp();
+}
+
+// pv_mcts.py:46-48: np.sum over the float32 legal policies = numpy's pairwise summation, which for fewer than 128
+// addends is: 8 running sums over the leading multiple of 8 (element i goes to sum i % 8), combined as
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the remaining addends one by one; fewer than 8 addends: serially from 0.
+// lp0/lp1/lp2 hold the legal policies in legal order (rank lane, lane + 32, lane + 64).
+__device__ float numpy_sum_f32(float lp0, float lp1, float lp2, int L, int lane) {
+    auto at = [&](int i) {                                            // warp-uniform i
+        const float src = i < 32 ? lp0 : (i < 64 ? lp1 : lp2);
+        return __shfl_sync(FULL, src, i & 31);
+    };
+    if (L < 8) {
+        float res = 0.0f;
+        for (int i = 0; i < L; i++) res = __fadd_rn(res, at(i));
+        return res;
+    }
+    const int nfull = L - (L % 8);
+    float r = __shfl_sync(FULL, lp0, lane & 7);                        // lanes 0..7: the 8 running sums
+    for (int b = 8; b < nfull; b += 8) {
+        const float src = b < 32 ? lp0 : (b < 64 ? lp1 : lp2);         // (b + j) >> 5 == b >> 5 for j < 8
+        r = __fadd_rn(r, __shfl_sync(FULL, src, (b + (lane & 7)) & 31));
+    }
+    float r0 = __shfl_sync(FULL, r, 0), r1 = __shfl_sync(FULL, r, 1), r2 = __shfl_sync(FULL, r, 2), r3 = __shfl_sync(FULL, r, 3);
+    float r4 = __shfl_sync(FULL, r, 4), r5 = __shfl_sync(FULL, r, 5), r6 = __shfl_sync(FULL, r, 6), r7 = __shfl_sync(FULL, r, 7);
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), __fadd_rn(r2, r3)), __fadd_rn(__fadd_rn(r4, r5), __fadd_rn(r6, r7)));
+    for (int i = nfull; i < L; i++) res = __fadd_rn(res, at(i));
+    return res;
+}
+
+// pv_mcts.py:105-109,157-160 for the k queued copies of one leaf: every copy REPLACES the child list (one list survives),
+// priors = policy[legal] / np.sum(policy[legal]) in float32 (pv_mcts.py:45-49), k sequential backups
+__device__ void apply_leaf_py(const TreeParams& P, const TreeView& T, TreeCtl& c, const PackedState& st, int lane) {
+    uint32_t lm[3];
+    int L = legal_mask(st, lm);
+    int k = c.pend_k, plen = c.path_len;
+    int leaf = T.path[plen - 1];
+    int base = c.n_nodes;
+    if (base + L > P.node_cap) {
+        if (lane == 0) atomicExch(P.counters + 5, 1ull);
+        c.phase = PHASE_DONE;
+        return;
+    }
+    size_t row = (size_t)c.nn_row * (size_t)P.row_stride;
+    const float* pol = P.policy + row * 81;
+    float p0 = __ldg(pol + lane), p1 = __ldg(pol + 32 + lane), p2 = (lane < 17) ? __ldg(pol + 64 + lane) : 0.0f;
+    // legal policies in legal order: rank i sits in lane i % 32, register i / 32
+    float lp[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int i = lane + 32 * j;
+        const int a = (i < L) ? nth_legal(lm, i) : 0;
+        const float v0 = __shfl_sync(FULL, p0, a & 31), v1 = __shfl_sync(FULL, p1, a & 31), v2 = __shfl_sync(FULL, p2, a & 31);
+        lp[j] = (i < L) ? (a < 32 ? v0 : (a < 64 ? v1 : v2)) : 0.0f;
+    }
+    const float sum = numpy_sum_f32(lp[0], lp[1], lp[2], L, lane);
+    const float uni = (L > 0) ? __fdiv_rn(1.0f, (float)L) : 0.0f;      // pv_mcts.py:50-56 (float64 there; unreachable with a softmax)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        const int i = lane + 32 * j;
+        if (i < L) T.node[base + i] = make_node(nth_legal(lm, i), (sum > 0.0f) ? __fdiv_rn(lp[j], sum) : uni);
+    }
+    if (lane == 0) T.node[leaf].w = (uint32_t)base | ((uint32_t)L << 20);
+    c.n_nodes = base + L;
+    backup(T, plen, k, P.value + row, 0, 0.0f, lane);
+    c.sims_left -= k;
+    c.pend_k = 0;
+    if (lane == 0) atomicAdd(P.counters + 3, (unsigned long long)k);
 }
 
 // cpp/uttt_mcts.cpp:138-167 for the k queued copies of one leaf
@@ -172,7 +249,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
     TreeView T = view_of(P, t);
 
     if (c.phase == PHASE_PENDING) {
-        apply_leaf(P, T, c, warp_load_state_finish(leaf_raw), lane);
+        if (P.flags & UTTT_SP_PYSEARCH) apply_leaf_py(P, T, c, warp_load_state_finish(leaf_raw), lane);
+        else apply_leaf(P, T, c, warp_load_state_finish(leaf_raw), lane);
         if (c.phase == PHASE_DONE) {
             if (lane == 0) { P.ctl[t] = c; if (P.slot_flags) P.slot_flags[t] = 0; }
             return;

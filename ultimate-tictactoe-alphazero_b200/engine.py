@@ -13,8 +13,22 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libuttt_b200.so")
 
 EVAL_NET_BF16, EVAL_NET_FP32, EVAL_HASH, EVAL_HOST, EVAL_NET_BF16X3 = 0, 1, 2, 3, 4
+NUMERICS = {"bf16": EVAL_NET_BF16, "bf16x3": EVAL_NET_BF16X3, "fp32": EVAL_NET_FP32}
+
+
+def evaluator_of(numerics):
+    """"bf16x3" (default of the drop-in modules: split-bf16 tcgen05 trunk, within 1e-2 of the fp32 reference forward on any
+    weights), "bf16" (plain bf16 operands: 3x the throughput, within 1e-2 on trained weights only), "fp32" (CUDA cores)"""
+    try:
+        return NUMERICS[numerics]
+    except KeyError:
+        raise ValueError("numerics must be one of %s, not %r" % (sorted(NUMERICS), numerics)) from None
+
+
+DEFAULT_NUMERICS = os.environ.get("UTTT_NUMERICS", "bf16x3")
 SP_CORRECT_TERMINAL_SIGN = 1
 SP_THROUGHPUT = 2
+SP_PYSEARCH = 4
 
 _vp = C.c_void_p
 _u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
@@ -64,6 +78,8 @@ ABI = {
     "uttt_mcts_search": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp],
                          C.c_int),
     "uttt_set_root_noise": ([_vp, C.c_float, C.c_float], C.c_int),
+    "uttt_set_selfplay_temperature": ([_vp, C.c_float], C.c_int),
+    "uttt_set_progress_callback": ([_vp, _vp, _vp], C.c_int),
     "uttt_mcts_begin": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32], C.c_int),
     "uttt_mcts_advance": ([_vp, C.POINTER(C.c_int32)], C.c_int),
     "uttt_mcts_get_leaves": ([_vp, _vp, _vp, _vp], C.c_int),
@@ -83,6 +99,7 @@ ABI = {
     "uttt_debug_trace_read": ([_vp, C.c_int64, C.POINTER(C.c_int64), _vp, _vp, _vp, _vp], C.c_int),
 }
 
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_int64, C.c_int64, _vp)
 _lib = None
 
 
@@ -346,6 +363,15 @@ class Engine:
     def set_root_noise(self, alpha=0.3, eps=0.25):
         """Dirichlet root noise of the throughput mode (eps=0 disables)"""
         _check(self.lib.uttt_set_root_noise(self.h, float(alpha), float(eps)))
+
+    def set_progress_callback(self, fn=None):
+        """fn(done, total) is called from inside selfplay() whenever the number of finished games has changed"""
+        self._progress = PROGRESS_FN(lambda done, total, user: fn(int(done), int(total))) if fn is not None else None
+        _check(self.lib.uttt_set_progress_callback(self.h, C.cast(self._progress, _vp) if self._progress else None, None))
+
+    def set_selfplay_temperature(self, temperature=1.0):
+        """SP_TEMPERATURE of the self-play loop (1: the reference's setting; 0: always the most visited move)"""
+        _check(self.lib.uttt_set_selfplay_temperature(self.h, float(temperature)))
 
     def mcts_search(self, roots, sims, batch, temperature, evaluator, flags=0):
         roots = np.ascontiguousarray(roots, dtype=np.uint32).reshape(-1, 8)

@@ -3,10 +3,11 @@ printed lines and promotion rule (evaluate_network.py:22-23,62-104), but the EN_
 CONCURRENTLY: at every ply all positions in which the same network is to move are searched as one batch on the
 GPU (uttt_mcts_search), so a 50-game match costs ~160 batched searches instead of ~2,900 sequential ones.
 
-Search semantics: the reference's gating match calls the pure-Python pv_mcts.pv_mcts_action; this version uses
-the reference's C++ search semantics (cpp/uttt_mcts.cpp:84-196, reproduced bit-exactly by the engine) with the
-same 50 simulations / batch 8 -- the two differ (component 12), and the faster path that
-train_cycle.py already uses for self-play is the one followed here.
+Search semantics: the reference's gating match calls the pure-Python pv_mcts.pv_mcts_action (evaluate_network.py:73-75),
+whose search differs from the C++ one used for self-play (evaluated root, replaced child lists, np.sum renormalisation,
+float64 scores; pv_mcts.py:74-180).  EN_SEARCH = "python" (default) runs exactly that search on the engine
+(UTTT_SP_PYSEARCH; pinned bit-exactly against the unmodified pv_mcts.py by tests/golden/pymcts.npz); EN_SEARCH = "cpp"
+selects the C++ semantics (cpp/uttt_mcts.cpp:84-196) instead.
 """
 from shutil import copy
 
@@ -22,6 +23,8 @@ EN_TEMPERATURE = 1.0      # evaluate_network.py:23
 PV_EVALUATE_COUNT = 50    # pv_mcts.py:16
 MCTS_BATCH_SIZE = 8       # pv_mcts.py:17
 EN_SEED = None            # None: derived from numpy's global RNG
+EN_SEARCH = "python"      # "python": pv_mcts.py semantics (what the reference's gating match runs); "cpp": uttt_mcts.cpp semantics
+EN_NUMERICS = _eng.DEFAULT_NUMERICS    # "bf16x3" | "bf16" | "fp32" (engine.evaluator_of)
 
 
 def first_player_point(ended_state):
@@ -31,19 +34,48 @@ def first_player_point(ended_state):
     return 0.5
 
 
+def python_scores(counts, temperature):
+    """pv_mcts.py:166-180 on the root visit counts: one-hot at np.argmax for T == 0, else boltzman in Python floats"""
+    if temperature == 0:
+        scores = np.zeros(len(counts))
+        scores[int(np.argmax(counts))] = 1
+        return scores
+    xs = [int(x) ** (1 / temperature) for x in counts]
+    total = sum(xs)
+    return np.array([x / total for x in xs])
+
+
+def pv_mcts_scores_batch(engine, roots, temperature, evaluator, search=None, evaluate_count=None, batch_size=None):
+    """the gating match's search for many positions at once -> (scores (n,81) float64 in legal order, n_legal (n,))"""
+    search = EN_SEARCH if search is None else search
+    sims = PV_EVALUATE_COUNT if evaluate_count is None else evaluate_count
+    batch = MCTS_BATCH_SIZE if batch_size is None else batch_size
+    if search == "cpp":
+        sc, _, ns = engine.mcts_search(roots, sims, batch, temperature, evaluator)
+        return sc.astype(np.float64), ns
+    if search != "python":
+        raise ValueError("EN_SEARCH must be 'python' or 'cpp', not %r" % (search,))
+    _, counts, ns = engine.mcts_search(roots, sims, batch, 1.0, evaluator, flags=_eng.SP_PYSEARCH)
+    sc = np.zeros((len(ns), 81), np.float64)
+    for i, n in enumerate(ns):
+        if n:
+            sc[i, :n] = python_scores(counts[i, :n], temperature)
+    return sc, ns
+
+
 class NetworkActor:
     """one side of a match: a DualNetwork evaluated by its own engine"""
 
-    def __init__(self, model, temperature, n_slots):
+    def __init__(self, model, temperature, n_slots, numerics=None, search=None):
+        self.evaluator = _eng.evaluator_of(EN_NUMERICS if numerics is None else numerics)
+        self.search = EN_SEARCH if search is None else search
         self.engine = _eng.Engine(n_slots=n_slots, max_sims=PV_EVALUATE_COUNT, max_batch=MCTS_BATCH_SIZE, max_games=1)
         model.eval()
         self.engine.upload_model(model)
         self.temperature = temperature
 
     def scores(self, roots):
-        sc, _, ns = self.engine.mcts_search(roots, PV_EVALUATE_COUNT, MCTS_BATCH_SIZE, self.temperature,
-                                            _eng.EVAL_NET_BF16)
-        return sc, ns
+        return pv_mcts_scores_batch(self.engine, roots, self.temperature, self.evaluator, self.search)
 
     def close(self):
         self.engine.close()
@@ -90,8 +122,10 @@ def play_matches(actors, n_games, seed):
             acts = np.zeros(len(sel), np.int32)
             for j, g in enumerate(sel):
                 legal = [x for x in range(81) if (masks[j, x // 27] >> (x % 27)) & 1]
-                p = sc[j, :ns[j]].astype(np.float64)
-                p = p / p.sum()
+                p = sc[j, :ns[j]]
+                if p.dtype != np.float64:                 # float32 scores of the C++ semantics (pv_mcts_cpp.py:129-133)
+                    p = p.astype(np.float64)
+                    p = p / p.sum()
                 acts[j] = rngs[g].choice(legal, p=p)
             nxt = _eng.game_step(st_d, torch.from_numpy(acts).to(dev))
             _, status = _eng.game_legal_mask(nxt)

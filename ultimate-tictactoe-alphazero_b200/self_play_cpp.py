@@ -29,7 +29,10 @@ PV_EVALUATE_COUNT = 50    # self_play_cpp.py:30
 MCTS_BATCH_SIZE = 8       # self_play_cpp.py:31
 
 # knobs that do not exist in the reference (defaults reproduce it)
-SP_NUMERICS = "bf16"          # "bf16" (tcgen05 trunk) or "fp32" (CUDA-core parity numerics)
+SP_NUMERICS = _eng.DEFAULT_NUMERICS   # "bf16x3" (split-bf16 tcgen05 trunk: within 1e-2 of the fp32 reference forward on
+                              # any weights), "bf16" (plain bf16 operands: 3x faster, within 1e-2 on trained weights) or
+                              # "fp32" (CUDA cores)
+SP_PROGRESS = True            # print the reference's per-game progress line (self_play_cpp.py:121) as games finish
 SP_MAX_SLOTS = 4096           # concurrent games per GPU
 SP_SEED = None                # None: draw from np.random
 CORRECTED_LABELS = False      # True: label from the true winner instead of self_play_cpp.py:95-99
@@ -71,8 +74,7 @@ def _history_arrays(eng, hist):
     legal_by_action[:, act_of_cell] = legal
     # scores over the legal actions: float32 n/sum (cpp/uttt_mcts.cpp:199-216, T=1) -> float64 renormalised
     # with numpy's own summation over exactly the legal entries (self_play_cpp.py:74-78), grouped by L
-    tot = cn.sum(axis=1).astype(np.float32)
-    sc32 = cn.astype(np.float32) / tot[:, None]
+    sc32 = _scores_from_counts(cn)
     pis = np.zeros((n, 81), np.float64)
     L = legal_by_action.sum(axis=1)
     for l in np.unique(L):
@@ -84,6 +86,19 @@ def _history_arrays(eng, hist):
     if CORRECTED_LABELS:
         z = _corrected_labels(hist)
     return xs, pis, z.astype(np.int64)
+
+
+def _scores_from_counts(cn):
+    """what pv_mcts_scores returns for these root visit counts at SP_TEMPERATURE (cpp/uttt_mcts.cpp:177-216): fp32
+    n / sum at T = 1, one-hot at the first maximum at T = 0, n^(1/T) / sum otherwise (zeros stay zeros)"""
+    x = cn.astype(np.float32)
+    if SP_TEMPERATURE == 0:
+        out = np.zeros_like(x)
+        out[np.arange(len(x)), x.argmax(axis=1)] = 1.0
+        return out
+    if SP_TEMPERATURE != 1.0:
+        x = np.power(x, np.float32(1.0) / np.float32(SP_TEMPERATURE), dtype=np.float32)
+    return x / x.sum(axis=1, dtype=np.float32)[:, None]
 
 
 def _corrected_labels(hist):
@@ -101,19 +116,30 @@ def _to_reference_format(xs, pis, zs):
     return [[xs[i], pis[i], int(zs[i])] for i in range(len(zs))]
 
 
-def _run(model, n_games):
+def _run(model, n_games, progress=False):
     eng = _get_engine(n_games)
     model.eval()
     eng.upload_model(model)
     seed = int(np.random.randint(0, 2 ** 31 - 1)) if SP_SEED is None else int(SP_SEED)
-    ev = _eng.EVAL_NET_FP32 if SP_NUMERICS == "fp32" else _eng.EVAL_NET_BF16
+    ev = _eng.evaluator_of(SP_NUMERICS)
     flags = _eng.SP_CORRECT_TERMINAL_SIGN if CORRECTED_TERMINAL_SIGN else 0
     if SP_SEARCH_MODE == "throughput":
         flags |= _eng.SP_THROUGHPUT
         eng.set_root_noise(SP_DIRICHLET_ALPHA, SP_DIRICHLET_EPS)
-    if SP_TEMPERATURE != 1.0:
-        raise NotImplementedError("the on-device sampler implements SP_TEMPERATURE == 1.0 (the reference's setting)")
-    hist = eng.selfplay(n_games, sims=PV_EVALUATE_COUNT, batch=MCTS_BATCH_SIZE, seed=seed, evaluator=ev, flags=flags)
+    eng.set_selfplay_temperature(SP_TEMPERATURE)
+    if SP_PROGRESS and progress:
+        shown = [0]
+
+        def progress(done, total):         # self_play_cpp.py:121, one line per finished game
+            for i in range(shown[0], done):
+                print(f"\rSelfPlay {i + 1}/{total} (Backend: C++)", end="")
+            shown[0] = done
+        eng.set_progress_callback(progress)
+    try:
+        hist = eng.selfplay(n_games, sims=PV_EVALUATE_COUNT, batch=MCTS_BATCH_SIZE, seed=seed, evaluator=ev, flags=flags)
+    finally:
+        eng.set_progress_callback(None)
+        eng.set_selfplay_temperature(1.0)
     last_stats.update(plies=int(hist.stats[0]), sims=int(hist.stats[1]), evals=int(hist.stats[2]),
                       rounds=int(hist.stats[3]), seed=seed)
     return eng, hist
@@ -142,9 +168,8 @@ def self_play(use_cpp=True):
     model = DualNetwork().to(device)
     model.load_state_dict(torch.load("./model/best.pth", map_location=device, weights_only=True))
     model.eval()
-    eng, hist = _run(model, SP_GAME_COUNT)
+    eng, hist = _run(model, SP_GAME_COUNT, progress=True)
     history = _to_reference_format(*_history_arrays(eng, hist))
-    print(f"\rSelfPlay {SP_GAME_COUNT}/{SP_GAME_COUNT} (Backend: C++)", end="")
     print("")
     now = datetime.now()
     file_name = "./data/{:04}{:02}{:02}{:02}{:02}{:02}.history".format(

@@ -5,6 +5,7 @@ libuttt_b200.so.  `State` is an immutable value object over the 32-byte packed p
 too when `model` is a DualNetwork, or with the caller's callable as evaluator otherwise.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -127,26 +128,39 @@ class State:
 # ------------------------------------------------------------------------------------------ search
 _engine = None
 _uploaded_key = None
-NUMERICS = "bf16"      # "bf16": tcgen05 trunk; "fp32": CUDA-core parity numerics
+_uploaded_model = None           # weakref to the module whose weights the engine holds
+NUMERICS = _eng.DEFAULT_NUMERICS   # "bf16x3" (default: split-bf16 tcgen05 trunk, within 1e-2 of the fp32 reference forward),
+                                 # "bf16" (plain bf16 operands, 3x faster), "fp32" (CUDA cores)
 
 
 def _get_engine(sims, batch):
-    global _engine, _uploaded_key
+    global _engine, _uploaded_key, _uploaded_model
     if _engine is None or _engine.max_sims < sims or _engine.max_batch < batch:
         if _engine is not None:
             _engine.close()
         _engine = _eng.Engine(n_slots=64, max_sims=max(sims, 50), max_batch=max(batch, 8), max_games=64)
         _uploaded_key = None
+        _uploaded_model = None
     return _engine
 
 
 def _sync_weights(e, model):
-    """upload the module's weights once per (module, parameter version)"""
-    global _uploaded_key
-    key = (id(model),) + tuple(t._version for t in model.state_dict().values())
-    if key != _uploaded_key:
+    """upload the module's weights unless the engine provably holds them already: the SAME live module object (a weak
+    reference: a new module that re-uses a dead one's address does not match) whose tensors have the same storage,
+    the same in-place version counters and the same content fingerprint of four of them"""
+    global _uploaded_key, _uploaded_model
+    import torch
+    sd = model.state_dict()
+    tensors = list(sd.values())
+    with torch.no_grad():          # a cheap content fingerprint of four tensors (writes through .data bump no version counter)
+        probe = [sd[k] for k in ("conv_input.weight", "residual_blocks.7.conv2.weight", "policy_fc.weight", "value_fc2.weight")
+                 if k in sd]
+        fp = torch.stack([t.reshape(-1)[:: max(1, t.numel() // 7)].double().sum() for t in probe]).cpu().numpy().tobytes()
+    key = (id(e), fp) + tuple((t.data_ptr(), t._version) for t in tensors)
+    if _uploaded_model is None or _uploaded_model() is not model or key != _uploaded_key:
         e.upload_model(model)
         _uploaded_key = key
+        _uploaded_model = weakref.ref(model)
 
 
 def _is_network(model):
@@ -170,7 +184,7 @@ def pv_mcts_scores(model, state, temperature=0.0, evaluate_count=50, batch_size=
     roots = state._w.reshape(1, 8)
     if _is_network(model):
         _sync_weights(e, model)
-        ev = _eng.EVAL_NET_FP32 if NUMERICS == "fp32" else _eng.EVAL_NET_BF16
+        ev = _eng.evaluator_of(NUMERICS)
         scores, _, ns = e.mcts_search(roots, evaluate_count, batch_size, temperature, ev)
         return scores[0, :ns[0]].tolist()
 
