@@ -208,6 +208,19 @@ int uttt_selfplay_run_device(uttt_engine *e, int64_t n_games, uint64_t game0, in
 int uttt_selfplay_fetch(uttt_engine *e, int64_t n_games, uint32_t *hist_states, uint16_t *hist_counts,
                         uint8_t *hist_actions, int32_t *hist_len, int8_t *hist_final);
 
+/* The history of the last uttt_selfplay_run_device as ONE contiguous device buffer of fixed-size samples (one per played
+ * ply, game-major order): bytes 0..31 packed position, 32..193 root visit counts u16[81], 194 z (int8, the label of
+ * self_play_cpp.py:95-99), 195 ply.  This is what a rank sends to the trainer rank in the multi-GPU cycle (one
+ * exact-length transfer instead of the ~1.7 KB/sample pickle of self_play_cpp.py:125-130).
+ * uttt_selfplay_pack: out_dev must hold cap_samples samples; *n_samples_out (HOST) = samples written; synchronises `stream`.
+ * uttt_samples_unpack (no engine needed): samples -> x (n,3,9,9) f32, policy (n,81) f32 = counts / sum, value (n) f32:
+ * the arrays train_network.py:41-60 builds from the pickle (policy in fp32 instead of the pickle's float64). */
+#define UTTT_SAMPLE_BYTES 196
+int uttt_selfplay_pack(uttt_engine *e, int64_t n_games, void *out_dev, int64_t cap_samples, int64_t *n_samples_out,
+                       void *stream);
+int uttt_samples_unpack(const void *samples_dev, int64_t n, float *x_dev, float *policy_dev, float *value_dev,
+                        void *stream);
+
 /* timing of the engine's own kernels during the last uttt_selfplay_run*: CUDA-event ms on the
  * launching stream and launch counts; kind: 0 tree kernels, 1 trunk, 2 heads, 3 everything */
 int uttt_last_run_profile(uttt_engine *e, int kind, double *ms_out, int64_t *launches_out);
@@ -224,6 +237,10 @@ int uttt_debug_trunk_timeline(uttt_engine *e, int64_t *out128);
 /* diagnostics: how many tensor-core trunk launches evaluated n positions, 64 buckets of 16 (bucket 63 = 1008 and
  * more), accumulated since creation or the last call with reset != 0 */
 int uttt_debug_batch_histogram(uttt_engine *e, int64_t *out64, int32_t reset);
+
+/* diagnostics: the device counters of the last search / self-play run: [2] plies, [3] simulations, [4] evaluated leaves,
+ * [5] node-arena overflow flag, [6] finished trees (search), [1] finished games (self-play) */
+int uttt_debug_counters(uttt_engine *e, uint64_t *out8);
 
 /* diagnostics for the parity tests: while enabled, uttt_mcts_search and uttt_selfplay_run* (reference-exact search only)
  * record every evaluated leaf with the evaluator rows its tree is about to consume -- (tree, game index, ply), packed leaf

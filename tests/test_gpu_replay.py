@@ -91,7 +91,7 @@ def test_slot_mode_search_replays_bit_exactly_in_every_band(nets, n_roots):
             same, p2, pol, v2, val = _search_and_replay(e, roots, 50, 8, engine.EVAL_NET_BF16, exact_rows=False)
             assert same.mean() > 0.5 and np.abs(p2 - pol).max() < 1e-3 and np.abs(v2 - val).max() < 3e-2
             wrong = np.roll(np.arange(len(val)), 1)                # what a row handed to the wrong tree would look like
-            assert np.median(np.abs(p2[wrong] - pol).max(1)) > 1e-3
+            assert np.median(np.abs(p2[wrong] - pol).max(1)) > 5 * np.abs(p2 - pol).max()
         # other search shapes of the same path
         for sims, batch, T in ((50, 1, 1.0), (37, 5, 0.0), (10, 2, 1.0)):
             _search_and_replay(e, roots[: min(n_roots, 96)], sims, batch, engine.EVAL_NET_BF16, exact_rows=False, temperature=T)

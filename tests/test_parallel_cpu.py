@@ -44,14 +44,28 @@ def _worker(rank, world, port, n_games, tmp):
             h.counts[i, :, :] = g % 50
         out = parallel.gather_histories(h, count, dst=0)
         if rank == 0:
-            assert out["lens"].shape == (n_games,)
-            assert (out["lens"] == 20 + np.arange(n_games) % 7).all()
-            assert (out["final"] == np.arange(n_games) % 2).all()
-            assert (out["states"][:, 5, 0] == np.arange(n_games)).all() and out["states"].dtype == np.uint32
-            assert (out["counts"][:, 3, 4] == np.arange(n_games) % 50).all()
+            lens = 20 + np.arange(n_games) % 7
+            gid = np.repeat(np.arange(n_games), lens)                 # global game id of every sample, game-major
+            ply = np.concatenate([np.arange(n) for n in lens])
+            assert out["states"].shape == (lens.sum(), 8) and out["states"].dtype == np.uint32
+            assert (out["states"][:, 0] == gid).all() and (out["ply"] == ply).all()
+            assert out["counts"].dtype == np.uint16 and (out["counts"] == (gid % 50)[:, None]).all()
+            z0 = np.where(gid % 2 != 0, -1, 0)                        # self_play_cpp.py:95-99
+            assert (out["z"] == z0 * np.where(ply % 2 == 0, 1, -1)).all()
+            sizes = [parallel.shard_games(n_games, world, r) for r in range(world)]
+            assert out["samples_per_rank"].tolist() == [int(lens[g0:g0 + c].sum()) for g0, c in sizes]
             open(os.path.join(tmp, "ok"), "w").write("ok")
         else:
             assert out is None
+        # exact-length transfer incl. an empty rank and a caller-provided destination buffer
+        mine = torch.full(((rank * 3) * engine.SAMPLE_BYTES,), rank + 1, dtype=torch.uint8)
+        dest = torch.zeros(10 * engine.SAMPLE_BYTES, dtype=torch.uint8) if rank == 1 else None
+        buf, counts = parallel.gather_samples(mine, dst=1, out=dest)
+        assert counts == [0, 3]
+        if rank == 1:
+            assert buf.data_ptr() == dest.data_ptr() and buf.numel() == 3 * engine.SAMPLE_BYTES and (buf == 2).all()
+        else:
+            assert buf is None
     finally:
         dist.destroy_process_group()
 

@@ -114,6 +114,12 @@ cudaError_t launch_scores(const int32_t* counts, const int32_t* n, int n_trees, 
                           float* scores, cudaStream_t s);
 cudaError_t launch_boltzman(const float* xs, int n, float temperature, float* out, cudaStream_t s);
 
+// history as fixed-size samples (history_kernels.cu)
+cudaError_t launch_scan_lens(const int32_t* lens, int64_t n, int64_t* offsets, cudaStream_t s);
+cudaError_t launch_pack_samples(const PackedState* states, const uint16_t* counts, const int32_t* lens, const int8_t* final_lose,
+                                const int64_t* offsets, int64_t n_games, void* out, int64_t cap_samples, cudaStream_t s);
+cudaError_t launch_unpack_samples(const void* samples, int64_t n, float* x, float* policy, float* value, cudaStream_t s);
+
 // ---------------------------------------------------------------- network
 struct NetWeights {
     // fp32 path: folded BN (scale into the weights, shift separate); layout [layer][tap][cin][cout]

@@ -83,6 +83,7 @@ struct uttt_engine {
     float* headfeat;        // [rows][243] head 1x1-conv outputs written by the tensor-core trunk
     float* tc_resid;        // [n_sm][32][512][4] fp32 residual stream of the tensor-core trunk (per CTA)
     int32_t* fwd_count;     // device int for uttt_net_forward
+    int64_t* hist_offsets;  // [max_games + 1] exclusive prefix sums of the game lengths (uttt_selfplay_pack)
     uint8_t* slot_flags;    // [n_slots] slot mode of the evaluator queue (see net_auto.cu)
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0, then [64] histogram of batch sizes (diagnostics)
     int prof_level;         // self-play kernel timing: 2 = tree / trunk / heads events every round, 1 = trunk only, 0 = none
@@ -315,7 +316,7 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         ealloc(e, &e->value, S * cfg->max_batch) || ealloc(e, &e->scores, S * 81) ||
         ealloc(e, &e->headfeat, R * 243) || ealloc(e, &e->act_a, R * 81 * 128) || ealloc(e, &e->act_b, R * 81 * 128) ||
         ealloc(e, &e->tc_resid, (size_t)N_LANES * e->n_sm * 512 * 64) || ealloc(e, &e->fwd_count, 1) || ealloc(e, &e->tc_dbg, 128 + 64 + 8 + 16) ||
-        ealloc(e, &e->slot_flags, S)) {
+        ealloc(e, &e->slot_flags, S) || ealloc(e, &e->hist_offsets, G + 1)) {
         uttt_destroy(e);
         return 1;
     }
@@ -944,6 +945,30 @@ int uttt_selfplay_fetch(uttt_engine* e, int64_t n_games, uint32_t* hist_states, 
     return 0;
 }
 
+int uttt_selfplay_pack(uttt_engine* e, int64_t n_games, void* out_dev, int64_t cap_samples, int64_t* n_samples_out, void* stream) {
+    UTTT_CHECK(e && n_samples_out && n_games >= 0 && n_games <= e->cfg.max_games && (out_dev || cap_samples == 0), "bad argument");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
+    const TreeParams& t = e->tp;
+    *n_samples_out = 0;
+    if (n_games == 0) return 0;
+    UTTT_CUDA_OK(launch_scan_lens(t.hist_len, n_games, e->hist_offsets, s));
+    long long total = 0;
+    UTTT_CUDA_OK(cudaMemcpyAsync(&total, e->hist_offsets + n_games, sizeof(total), cudaMemcpyDeviceToHost, s));
+    UTTT_CUDA_OK(cudaStreamSynchronize(s));
+    UTTT_CHECK(total <= cap_samples, "sample buffer too small: %lld samples, room for %lld", total, (long long)cap_samples);
+    UTTT_CUDA_OK(launch_pack_samples(t.hist_states, t.hist_counts, t.hist_len, t.hist_final, e->hist_offsets, n_games, out_dev,
+                                     cap_samples, s));
+    *n_samples_out = total;
+    return 0;
+}
+
+int uttt_samples_unpack(const void* samples_dev, int64_t n, float* x_dev, float* policy_dev, float* value_dev, void* stream) {
+    UTTT_CHECK(n >= 0 && (n == 0 || (samples_dev && x_dev && policy_dev && value_dev)), "bad argument");
+    UTTT_CUDA_OK(launch_unpack_samples(samples_dev, n, x_dev, policy_dev, value_dev, (cudaStream_t)stream));
+    return 0;
+}
+
 int uttt_selfplay_run(uttt_engine* e, int64_t n_games, uint64_t game0, int32_t sims, int32_t batch, uint32_t seed,
                       int32_t evaluator, int32_t flags, uint32_t* hist_states, uint16_t* hist_counts,
                       uint8_t* hist_actions, int32_t* hist_len, int8_t* hist_final, int64_t* stats) {
@@ -1007,6 +1032,14 @@ int uttt_debug_trace_read(uttt_engine* e, int64_t cap, int64_t* n_out, int32_t* 
         memcpy(policy + 81 * i, r.policy, 81 * 4);
         value[i] = r.value;
     }
+    return 0;
+}
+
+int uttt_debug_counters(uttt_engine* e, uint64_t* out8) {
+    UTTT_CHECK(e && out8, "null argument");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    UTTT_CUDA_OK(cudaDeviceSynchronize());
+    UTTT_CUDA_OK(cudaMemcpy(out8, e->tp.counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -21,6 +21,27 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,
     trunk_tc2_body<LT, X3>(wq, wq_in, wq_bias, planes, headw, headfeat, skip, count, min_count, max_count, dbg);
 }
 
+// The split-bf16 trunk.  A pair's share of the batch, ceil(n / pairs) positions, is evaluated as consecutive groups of up
+// to 5 positions (2 + 2 accumulator tiles), each by one complete pass of the body (set-up and tear-down are ~1 % of a
+// pass here: every layer issues 3 x 72 MMAs per tile).  7 positions per pair -- the 500-game cycle -- cost 2 + 1 tile
+// times (groups of 5 and 2) instead of the 2 + 2 of two waves of 5-position groups over the whole grid.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<2, true>::THREADS, 1)
+trunk_x3_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wq_in,
+                const __nv_bfloat16* __restrict__ wq_bias, const __nv_bfloat16* __restrict__ planes,
+                const float* __restrict__ headw, float* headfeat, uint4* skip, const int32_t* __restrict__ count,
+                long long* dbg) {
+    const int n_pos = *count;
+    if (n_pos <= 0) return;
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0)          // diagnostics: histogram of evaluator batch sizes (16 per bucket)
+        atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 128 + min(n_pos >> 4, 63), 1ull);
+    const int n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+    const int per_pair = (n_pos + n_pairs - 1) / n_pairs;
+    const int first = pair * per_pair, last = min(n_pos, first + per_pair);
+    for (int off = first; off < last; off += Cfg<2, true>::MAX_P)
+        trunk_tc2_body<2, true>(wq, wq_in, wq_bias, planes, headw, headfeat, skip, count, 0, 0x7FFFFFFF, nullptr,
+                                min(Cfg<2, true>::MAX_P, last - off), nullptr, off, true);
+}
+
 }  // namespace tc2
 
 
@@ -28,8 +49,7 @@ cudaError_t trunk_tc2_init() {
     cudaError_t e = cudaFuncSetAttribute(tc2::trunk_tc2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          tc2::Cfg<2, false>::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(tc2::trunk_tc2_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                tc2::Cfg<2, true>::SMEM_BYTES);
+    return cudaFuncSetAttribute(tc2::trunk_x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::Cfg<2, true>::SMEM_BYTES);
 }
 
 int trunk_tc2_small_capacity(int n_sm) { return (n_sm / 2) * tc2::Cfg<2>::MAX_P; }
@@ -44,15 +64,14 @@ cudaError_t launch_trunk_tc2_small(const NetWeights& w, const __nv_bfloat16* pla
     return cudaGetLastError();
 }
 
-// split-bf16 trunk: any batch size; groups of up to 5 positions per CTA pair, as many waves as the batch needs
+// split-bf16 trunk: any batch size in one launch (see trunk_x3_kernel)
 // (skip: 128 KiB per CTA, fp32)
 cudaError_t launch_trunk_x3(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count,
                             int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg) {
     int pairs = n_sm / 2;
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
-    tc2::trunk_tc2_kernel<2, true><<<2 * pairs, tc2::Cfg<2, true>::THREADS, tc2::Cfg<2, true>::SMEM_BYTES, s>>>(
-        w.res_w_x3, w.conv_in_w_x3, w.bias_blk_x3, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, 0,
-        0x7FFFFFFF, dbg);
+    tc2::trunk_x3_kernel<<<2 * pairs, tc2::Cfg<2, true>::THREADS, tc2::Cfg<2, true>::SMEM_BYTES, s>>>(
+        w.res_w_x3, w.conv_in_w_x3, w.bias_blk_x3, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, dbg);
     return cudaGetLastError();
 }
 

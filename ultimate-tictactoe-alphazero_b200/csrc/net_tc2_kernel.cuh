@@ -103,7 +103,9 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                  int min_count, int max_count,           // this launch handles min_count < batch <= max_count
                  long long* dbg,
                  int n_pos_known = -1,                   // >= 0: the batch size (slot mode: counted from the slot flags, `count` unused)
-                 const int* src_rows = nullptr) {        // slot mode: position i of this CTA pair reads planes row src_rows[i]
+                 const int* src_rows = nullptr,          // slot mode: position i of this CTA pair reads planes row src_rows[i]
+                 int pos_base = 0, bool solo = false) {  // solo: this CTA pair alone evaluates the n_pos_known positions that
+                                                         // start at row pos_base of planes / headfeat (trunk_x3_kernel)
     using C = Cfg<LT, X3>;
     constexpr int LOC_TILES = C::LOC_TILES, MAX_P = C::MAX_P, PANEL_BYTES = C::PANEL_BYTES, A_BYTES = C::A_BYTES,
                   STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS,
@@ -115,10 +117,10 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
     const long long t_entry = clock64();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_rank();
-    const int n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
+    const int n_pairs = solo ? 1 : (int)gridDim.x >> 1, pair = solo ? 0 : (int)blockIdx.x >> 1;
     const int n_pos = n_pos_known >= 0 ? n_pos_known : *count;
     if (n_pos <= min_count || n_pos > max_count) return;
-    if (dbg && blockIdx.x == 0 && threadIdx.x == 0)          // diagnostics: histogram of evaluator batch sizes (16 per bucket)
+    if (dbg && blockIdx.x == 0 && threadIdx.x == 0 && !solo) // diagnostics: histogram of evaluator batch sizes (16 per bucket)
         atomicAdd(reinterpret_cast<unsigned long long*>(dbg) + 128 + min(n_pos >> 4, 63), 1ull);
     const int P = group_positions<LT>(n_pos, n_pairs);
     const int T = (P * POS_ROWS + 127) / 128;         // tiles of the pair: 1..4
@@ -187,7 +189,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
             const int r = idx / 10, c = idx - 10 * r;
             const int gpos = g * P + pos;
             const bool valid = (pos < P) && (r < 9) && (c < 9) && (gpos < n_pos);
-            float* hrow = headfeat + (size_t)gpos * 243 + (size_t)(r * 9 + c);
+            float* hrow = headfeat + (size_t)(pos_base + gpos) * 243 + (size_t)(r * 9 + c);
             float4* hscr = reinterpret_cast<float4*>(smem + C::HEAD_OFF) + lr;
             uint4* srow_skip = skip + ((size_t)blockIdx.x * (16 * SKIP_ROWS) + (size_t)(chalf * 8) * SKIP_ROWS + (size_t)lr) * SKIP_U4;
             uint8_t* srow = sA + (size_t)(chalf * 8) * PANEL_BYTES + (size_t)(LEAD + lr) * 16;
@@ -223,7 +225,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
             {
                 uint4 pk = zero4;
                 if (chalf == 0 && valid) {
-                    const __nv_bfloat16* px = planes + (size_t)(src_rows ? src_rows[pos] : gpos) * 243 + (size_t)(r * 9 + c);
+                    const __nv_bfloat16* px = planes + (size_t)(src_rows ? src_rows[pos] : pos_base + gpos) * 243 + (size_t)(r * 9 + c);
                     uint32_t x0 = (uint32_t)__bfloat16_as_ushort(px[0]), x1 = (uint32_t)__bfloat16_as_ushort(px[81]),
                              x2 = (uint32_t)__bfloat16_as_ushort(px[162]);
                     pk = make_uint4(x0 | (x1 << 16), x2, 0u, 0u);
@@ -512,6 +514,9 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
     cluster_sync_all();                 // nobody exits while the peer may still write its margins / barriers
     if (warp == EPI_WARPS + 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+    }
+    if (solo && threadIdx.x == 0) {     // the body runs again in this launch: leave no valid mbarrier objects behind
+        for (uint32_t b = bar_u; b < bar_bnd + 8; b += 8) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b) : "memory");
     }
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0) dbg[195] = clock64();
 }

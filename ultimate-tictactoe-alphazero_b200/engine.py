@@ -91,10 +91,13 @@ ABI = {
     "uttt_selfplay_run_device": ([_vp, C.c_int64, C.c_uint64, C.c_int32, C.c_int32, C.c_uint32, C.c_int32,
                                   C.c_int32, _vp, _vp], C.c_int),
     "uttt_selfplay_fetch": ([_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp], C.c_int),
+    "uttt_selfplay_pack": ([_vp, C.c_int64, _vp, C.c_int64, C.POINTER(C.c_int64), _vp], C.c_int),
+    "uttt_samples_unpack": ([_vp, C.c_int64, _vp, _vp, _vp, _vp], C.c_int),
     "uttt_debug_trunk_timeline": ([_vp, _vp], C.c_int),
     "uttt_debug_batch_histogram": ([_vp, _vp, C.c_int32], C.c_int),
     "uttt_last_run_profile": ([_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
     "uttt_set_profile_level": ([_vp, C.c_int], C.c_int),
+    "uttt_debug_counters": ([_vp, _vp], C.c_int),
     "uttt_debug_trace": ([_vp, C.c_int], C.c_int),
     "uttt_debug_trace_read": ([_vp, C.c_int64, C.POINTER(C.c_int64), _vp, _vp, _vp, _vp], C.c_int),
 }
@@ -253,6 +256,29 @@ def scattered_residual_tensors(sd):
         if tuple(t.shape) != shp:
             raise ValueError("state_dict tensor has shape %s, expected %s" % (tuple(t.shape), shp))
     return convs, bns
+
+
+SAMPLE_BYTES = 196      # UTTT_SAMPLE_BYTES: packed position 32 B, visit counts u16[81], z int8, ply u8
+
+
+def samples_unpack(samples, n=None, stream=None):
+    """device uint8 buffer of packed samples -> (x (n,3,9,9) f32, policy (n,81) f32, value (n,1) f32) CUDA tensors: the
+    arrays train_network.py:41-60 builds from the .history pickle"""
+    import torch
+    n = samples.numel() // SAMPLE_BYTES if n is None else int(n)
+    x = torch.empty((n, 3, 9, 9), dtype=torch.float32, device=samples.device)
+    p = torch.empty((n, 81), dtype=torch.float32, device=samples.device)
+    v = torch.empty((n, 1), dtype=torch.float32, device=samples.device)
+    _check(load_library().uttt_samples_unpack(_ptr(samples), n, _ptr(x), _ptr(p), _ptr(v), _stream(stream)))
+    return x, p, v
+
+
+def samples_to_numpy(samples):
+    """host view of packed samples: (states (n,8) u32, counts (n,81) u16, z (n,) i8, ply (n,) u8)"""
+    raw = np.ascontiguousarray(samples).view(np.uint8).reshape(-1, SAMPLE_BYTES)
+    st = raw[:, :32].copy().view(np.uint32)
+    cn = raw[:, 32:194].copy().view(np.uint16)
+    return st, cn, raw[:, 194].copy().view(np.int8), raw[:, 195].copy()
 
 
 class History:
@@ -437,6 +463,18 @@ class Engine:
                                             _ptr(hist.lens), _ptr(hist.final)))
         return hist
 
+    def selfplay_pack(self, n_games, out=None, stream=None):
+        """history of the last selfplay_device() as one device buffer of SAMPLE_BYTES-byte samples -> (uint8 CUDA tensor
+        sliced to the exact length, n_samples).  `out`: optional uint8 CUDA tensor to pack into (81 * n_games samples fit)"""
+        import torch
+        cap = 81 * int(n_games)
+        if out is None:
+            out = torch.empty(cap * SAMPLE_BYTES, dtype=torch.uint8, device=torch.device("cuda", self.device))
+        cap = out.numel() // SAMPLE_BYTES
+        n = C.c_int64(0)
+        _check(self.lib.uttt_selfplay_pack(self.h, int(n_games), _ptr(out), cap, C.byref(n), _stream(stream)))
+        return out[: n.value * SAMPLE_BYTES], n.value
+
     def trunk_timeline(self):
         """clock64 stamps of CTA 0 of the last tcgen05 trunk launch: (32,4) = MMA start, MMA issued,
         accumulators ready, epilogue done"""
@@ -449,6 +487,13 @@ class Engine:
         out = np.zeros(64, np.int64)
         _check(self.lib.uttt_debug_batch_histogram(self.h, _ptr(out), 1 if reset else 0))
         return out
+
+    def counters(self):
+        """device counters of the last search / self-play run: dict(plies, sims, evals, overflow, finished_trees, finished_games)"""
+        out = np.zeros(8, np.uint64)
+        _check(self.lib.uttt_debug_counters(self.h, _ptr(out)))
+        return {"finished_games": int(out[1]), "plies": int(out[2]), "sims": int(out[3]), "evals": int(out[4]),
+                "overflow": int(out[5]), "finished_trees": int(out[6])}
 
     def trace(self, enable=True):
         """start (and clear) / stop recording every evaluated leaf of the reference-exact search (diagnostics, slow)"""

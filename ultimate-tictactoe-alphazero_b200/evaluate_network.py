@@ -46,13 +46,14 @@ def python_scores(counts, temperature):
 
 
 def pv_mcts_scores_batch(engine, roots, temperature, evaluator, search=None, evaluate_count=None, batch_size=None):
-    """the gating match's search for many positions at once -> (scores (n,81) float64 in legal order, n_legal (n,))"""
+    """the gating match's search for many positions at once -> (scores (n,81) in legal order, n_legal (n,)); float64
+    probabilities with the Python semantics, float32 scores with the C++ ones"""
     search = EN_SEARCH if search is None else search
     sims = PV_EVALUATE_COUNT if evaluate_count is None else evaluate_count
     batch = MCTS_BATCH_SIZE if batch_size is None else batch_size
     if search == "cpp":
         sc, _, ns = engine.mcts_search(roots, sims, batch, temperature, evaluator)
-        return sc.astype(np.float64), ns
+        return sc, ns                  # float32, renormalised in float64 by the caller (pv_mcts_cpp.py:129-133)
     if search != "python":
         raise ValueError("EN_SEARCH must be 'python' or 'cpp', not %r" % (search,))
     _, counts, ns = engine.mcts_search(roots, sims, batch, 1.0, evaluator, flags=_eng.SP_PYSEARCH)

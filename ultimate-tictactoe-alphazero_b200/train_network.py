@@ -167,11 +167,14 @@ def _graphed_epochs(model, xs, y_policies, y_values, epochs, batch_size, bf16, l
 
 def train_tensors(model, xs, y_policies, y_values, epochs=None, batch_size=None, bf16=None, graph=None, log=print):
     """The training loop of train_network.py:89-113 over device-resident tensors.  Returns the per-epoch mean losses.
-    graph (default: on for CUDA tensors, `UTTT_TRAIN_GRAPH=0` turns it off): replay the step as a CUDA graph."""
+    graph (opt-in: `UTTT_TRAIN_GRAPH=1` or graph=True; CUDA tensors only): replay the step as a CUDA graph with
+    Adam(capturable=True).  The default is the eager loop, whose arithmetic is the reference trainer's (bit-identical
+    weights on the CPU, tests/test_train_cpu.py); the graph path orders Adam's arithmetic differently (same losses to
+    ~4 digits, tools/train_equiv.py) and needs torch >= 2.1 (tensor learning rate)."""
     epochs = RN_EPOCHS if epochs is None else epochs
     batch_size = BATCH_SIZE if batch_size is None else batch_size
     bf16 = (os.environ.get("UTTT_TRAIN_BF16", "0") == "1") if bf16 is None else bf16
-    graph = (os.environ.get("UTTT_TRAIN_GRAPH", "1") == "1") if graph is None else graph
+    graph = (os.environ.get("UTTT_TRAIN_GRAPH", "0") == "1") if graph is None else graph
     if bf16:
         model = model.to(memory_format=torch.channels_last)
         xs = xs.contiguous(memory_format=torch.channels_last)
@@ -183,7 +186,9 @@ def train_tensors(model, xs, y_policies, y_values, epochs=None, batch_size=None,
 def load_tensors():
     """the newest cycle's samples as device tensors: from the packed sidecar `<timestamp>.packed.npz` of the newest
     `.history` file if self-play wrote one (self_play_cpp.SP_WRITE_PACKED; 357 B per sample, planes re-encoded on the
-    GPU), else from the reference's pickle itself"""
+    GPU), else from the reference's pickle itself.  The sidecar's policy targets are fp32 counts / sum; the pickle's are
+    that value re-normalised in float64 and cast back (self_play_cpp.py:74-78 -> train_network.py:51): equal to ~1e-7,
+    not bit for bit -- delete the sidecar (or leave SP_WRITE_PACKED off, the default) for the reference's exact targets."""
     history_path = sorted(Path("./data").glob("*.history"))[-1]
     sidecar = Path(str(history_path).replace(".history", ".packed.npz"))
     if sidecar.exists() and device.type == "cuda":
