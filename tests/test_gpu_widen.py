@@ -169,3 +169,26 @@ def test_trainer_dropin_on_gpu(tmp_path, monkeypatch):
     assert not torch.equal(sd["conv_input.weight"].cpu(), model.state_dict()["conv_input.weight"].cpu())
     model2 = DualNetwork()
     model2.load_state_dict(sd)                       # loadable by the engine / the next self-play cycle
+
+
+def test_train_cycle_iteration(tmp_path, monkeypatch, capsys):
+    """one iteration of the train_cycle driver (train_cycle.py:20-41: self-play -> train -> gating match -> vs-random) through
+    the drop-in modules, reduced sizes, the reference's file protocol in a scratch directory"""
+    import torch
+    import self_play_cpp
+    import train_network as tn
+    import evaluate_network as en
+    import evaluate_best_player as ep
+    import train_cycle
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(self_play_cpp, "SP_GAME_COUNT", 16)
+    monkeypatch.setattr(tn, "RN_EPOCHS", 2)
+    monkeypatch.setattr(en, "EN_GAME_COUNT", 4)
+    monkeypatch.setattr(ep, "EP_GAME_COUNT", 2)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    train_cycle.train_cycle(cycles=1)
+    out = capsys.readouterr().out
+    assert "Train 0 ====" in out and "SelfPlay 16/16 (Backend: C++)" in out and ">> Train 0" in out and "AveragePoint" in out
+    assert (tmp_path / "model" / "best.pth").exists() and (tmp_path / "model" / "latest.pth").exists()
+    assert len(list((tmp_path / "data").glob("*.history"))) == 1

@@ -74,6 +74,11 @@ struct uttt_engine {
     cudaStream_t stream;
     cudaStream_t lane_stream[N_LANES];
     cudaEvent_t ev_fork, ev_join[N_LANES], ev_win[N_WINDOWS][N_LANES];
+    // uttt_net_forward runs on the CALLER's stream but works in the engine's evaluator buffers: ev_fwd marks the end of the
+    // last forward (the engine's own streams wait for it before they touch those buffers), ev_idle the point the engine's
+    // stream had reached when a forward started (the forward waits for it)
+    cudaEvent_t ev_fwd, ev_idle;
+    bool fwd_pending;
     TreeParams tp;          // device pointers (n_trees / mode / sims set per call)
     float* policy;          // [n_slots*max_batch][81]
     float* value;           // [n_slots*max_batch]
@@ -146,6 +151,15 @@ EvalBufs bufs_of(uttt_engine* e, size_t first_slot, int lane) {
     b.slot_flags = nullptr;
     b.n_slots = 0;
     return b;
+}
+
+// work about to be enqueued on `s` touches the evaluator buffers / weights: order it behind an unfinished uttt_net_forward
+int wait_for_forward(uttt_engine* e, cudaStream_t s) {
+    if (e->fwd_pending) {
+        UTTT_CUDA_OK(cudaStreamWaitEvent(s, e->ev_fwd, 0));
+        e->fwd_pending = false;
+    }
+    return 0;
 }
 
 int run_evaluator(uttt_engine* e, const EvalBufs& b, int evaluator, const int32_t* count, int max_rows, cudaStream_t s,
@@ -329,6 +343,9 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
         for (int w = 0; w < N_WINDOWS; w++) UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_win[w][i], cudaEventDisableTiming));
     }
     UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_fwd, cudaEventDisableTiming));
+    UTTT_CUDA_OK(cudaEventCreateWithFlags(&e->ev_idle, cudaEventDisableTiming));
+    e->fwd_pending = false;
     UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_counters, 8 * (1 + N_WINDOWS) * sizeof(unsigned long long)));
     UTTT_CUDA_OK(cudaMallocHost((void**)&e->h_count, 2 * sizeof(int32_t)));
     for (int i = 0; i < EV_POOL; i++) UTTT_CUDA_OK(cudaEventCreate(&e->ev[i]));
@@ -368,6 +385,8 @@ int uttt_destroy(uttt_engine* e) {
         for (int w = 0; w < N_WINDOWS; w++) if (e->ev_win[w][i]) cudaEventDestroy(e->ev_win[w][i]);
     }
     if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+    if (e->ev_fwd) cudaEventDestroy(e->ev_fwd);
+    if (e->ev_idle) cudaEventDestroy(e->ev_idle);
     delete e;
     return 0;
 }
@@ -396,6 +415,10 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
                        const float* const (*res_bn_tab)[4]) {
     UTTT_CHECK(e && w, "null argument");
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
+    if (e->fwd_pending) {          // (the upload is synchronous and partly uses blocking copies: wait on the host)
+        UTTT_CUDA_OK(cudaEventSynchronize(e->ev_fwd));
+        e->fwd_pending = false;
+    }
     auto fetch = [&](const float* p, size_t n, std::vector<float>& v) -> int {
         v.resize(n);
         UTTT_CHECK(p != nullptr, "null weight tensor");
@@ -583,6 +606,9 @@ int uttt_net_forward(uttt_engine* e, const uint32_t* states_dev, int64_t n, int 
                "mode must be UTTT_EVAL_NET_BF16, _BF16X3 or _FP32");
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     cudaStream_t s = (cudaStream_t)stream;
+    // the engine's own stream may still be uploading weights or finishing a search in the same buffers
+    UTTT_CUDA_OK(cudaEventRecord(e->ev_idle, e->stream));
+    UTTT_CUDA_OK(cudaStreamWaitEvent(s, e->ev_idle, 0));
     for (int64_t off = 0; off < n; off += e->cfg.n_slots) {
         int m = (int)((n - off < e->cfg.n_slots) ? (n - off) : e->cfg.n_slots);
         if (uttt_game_gather_planes(states_dev + off * 8, e->tp.nn_planes, m, s)) return 1;
@@ -592,6 +618,8 @@ int uttt_net_forward(uttt_engine* e, const uint32_t* states_dev, int64_t n, int 
                                      cudaMemcpyDeviceToDevice, s));
         UTTT_CUDA_OK(cudaMemcpyAsync(value_dev + off, e->value, (size_t)m * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
+    UTTT_CUDA_OK(cudaEventRecord(e->ev_fwd, s));
+    e->fwd_pending = true;
     return 0;
 }
 
@@ -605,6 +633,7 @@ static int mcts_begin_impl(uttt_engine* e, const uint32_t* roots, int32_t n_root
     e->s_n_roots = n_roots; e->s_sims = sims; e->s_batch = batch; e->s_round = 0; e->s_pending = 0;
     e->s_per_copy = 0; e->s_have_results = 0;
     if (n_roots == 0) return 0;
+    if (wait_for_forward(e, e->stream)) return 1;
     UTTT_CUDA_OK(cudaMemcpyAsync(t.root, roots, (size_t)n_roots * 32, cudaMemcpyHostToDevice, e->stream));
     UTTT_CUDA_OK(cudaMemsetAsync(t.counters, 0, 8 * sizeof(unsigned long long), e->stream));
     UTTT_CUDA_OK(launch_tree_begin(t, e->stream));
@@ -642,6 +671,7 @@ int uttt_mcts_advance(uttt_engine* e, int32_t* n_pending) {
 
 int uttt_mcts_get_leaves(uttt_engine* e, uint32_t* states, int32_t* k, int32_t* tree) {
     UTTT_CHECK(e, "null engine");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     int n = e->s_pending;
     if (n == 0) return 0;
     if (states) UTTT_CUDA_OK(cudaMemcpyAsync(states, e->tp.nn_states, (size_t)n * 32, cudaMemcpyDeviceToHost, e->stream));
@@ -653,6 +683,7 @@ int uttt_mcts_get_leaves(uttt_engine* e, uint32_t* states, int32_t* k, int32_t* 
 
 int uttt_mcts_put_results(uttt_engine* e, const float* policy, const float* value, int per_copy) {
     UTTT_CHECK(e && policy && value, "null argument");
+    UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     int n = e->s_pending;
     size_t rows = per_copy ? (size_t)n * e->cfg.max_batch : (size_t)n;
     UTTT_CUDA_OK(cudaMemcpyAsync(e->policy, policy, rows * 81 * sizeof(float), cudaMemcpyHostToDevice, e->stream));
@@ -781,6 +812,7 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     for (int i = 0; i < 4; i++) { e->prof_ms[i] = 0.0; e->prof_launches[i] = 0; }
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (n_games == 0) return 0;
+    if (wait_for_forward(e, s)) return 1;
     TreeParams& t = e->tp;
     t.sims = sims; t.batch = batch; t.mode = MODE_SELFPLAY; t.flags = flags;
     t.parity = 0; t.row_stride = 1; t.copy_stride = 0;

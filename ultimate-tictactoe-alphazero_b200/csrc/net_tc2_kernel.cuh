@@ -158,7 +158,8 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
                      "r"(C::TMEM_COLS)
                      : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        // (solo: the body runs again in this launch and allocates again -- a CTA that gave up its permit may not)
+        if (!solo) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int i = threadIdx.x; i < A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
