@@ -162,6 +162,11 @@ int uttt_set_root_noise(uttt_engine *e, float alpha, float eps);
  * moves are drawn from n^(1/T) / sum.  The history always holds the raw visit counts. */
 int uttt_set_selfplay_temperature(uttt_engine *e, float temperature);
 
+/* diagnostics: the root-noise sampler alone -- out[g][0..n_children) = the Dirichlet(alpha) draw that the throughput mode
+ * mixes into the root priors of game game0 + g at ply 0 (Philox key (seed, 3), counter (game, ply, child, attempt)) */
+int uttt_debug_dirichlet(uint32_t seed, uint64_t game0, int64_t n, int32_t n_children, float alpha, float *out_dev,
+                         void *stream);
+
 /* step-wise form for a caller-side evaluator (python_bindings.cpp:11-47 `wrap_python_inference`) */
 int uttt_mcts_begin(uttt_engine *e, const uint32_t *roots, int32_t n_roots, int32_t evaluate_count,
                     int32_t batch_size);

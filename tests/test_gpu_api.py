@@ -168,3 +168,31 @@ def _best():
     m = DualNetwork()
     m.load_state_dict(torch.load("./model/best.pth", weights_only=True))
     return m
+
+
+@pytest.mark.parametrize("alpha,L", [(0.3, 9), (0.3, 81), (1.0, 5), (0.1, 20), (2.5, 3)])
+def test_dirichlet_root_noise_distribution(alpha, L):
+    """the throughput mode's root noise (csrc/tree_tp_kernels.cu: Marsaglia-Tsang gammas from Philox, normalised) is
+    Dirichlet(alpha): moments against the closed forms, every marginal's mean, and a Kolmogorov-Smirnov test of one
+    marginal against Beta(alpha, (L-1) alpha) and against numpy's own sampler"""
+    import engine
+    from scipy import stats
+    n = 200000
+    x = engine.dirichlet_samples(17, 0, n, L, alpha).cpu().numpy().astype(np.float64)
+    assert np.isfinite(x).all() and (x >= 0).all() and np.abs(x.sum(1) - 1).max() < 1e-5
+    mean, var = 1.0 / L, (1.0 / L) * (1 - 1.0 / L) / (L * alpha + 1)
+    se_mean = np.sqrt(var / n)
+    assert np.abs(x.mean(0) - mean).max() < 6 * se_mean, (x.mean(0), mean)
+    assert abs(x[:, 0].var() - var) < 0.03 * var
+    cov01 = -(1.0 / L) ** 2 / (L * alpha + 1)                    # Cov(x_i, x_j) of a symmetric Dirichlet
+    assert abs(np.cov(x[:, 0], x[:, 1])[0, 1] - cov01) < 0.05 * abs(cov01) + 6 * var / np.sqrt(n)
+    for col in (0, L - 1):
+        d, p = stats.kstest(x[:, col], stats.beta(alpha, (L - 1) * alpha).cdf)
+        assert p > 1e-4 or d < 0.004, (col, d, p)
+    ref = np.random.RandomState(1).dirichlet([alpha] * L, size=n)[:, 0]
+    d2, p2 = stats.ks_2samp(x[:, 0], ref)
+    assert p2 > 1e-4 or d2 < 0.005, (d2, p2)
+    # a different seed / game range gives different, equally distributed draws; the same key the same draw
+    y = engine.dirichlet_samples(17, 0, 64, L, alpha).cpu().numpy()
+    z = engine.dirichlet_samples(18, 0, 64, L, alpha).cpu().numpy()
+    assert (y == x[:64].astype(np.float32)).all() and (y != z).any()

@@ -112,6 +112,7 @@ cudaError_t launch_hash_eval(const PackedState* states, const int32_t* k, const 
                              float* policy, float* value, int row_stride, int copy_stride, cudaStream_t s);
 cudaError_t launch_scores(const int32_t* counts, const int32_t* n, int n_trees, float temperature,
                           float* scores, cudaStream_t s);
+cudaError_t launch_dirichlet(uint32_t seed, uint64_t game0, int64_t n, int n_children, float alpha, float* out, cudaStream_t s);
 cudaError_t launch_boltzman(const float* xs, int n, float temperature, float* out, cudaStream_t s);
 
 // history as fixed-size samples (history_kernels.cu)

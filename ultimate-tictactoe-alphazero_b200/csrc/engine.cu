@@ -764,6 +764,12 @@ int uttt_set_root_noise(uttt_engine* e, float alpha, float eps) {
     return 0;
 }
 
+int uttt_debug_dirichlet(uint32_t seed, uint64_t game0, int64_t n, int32_t n_children, float alpha, float* out_dev, void* stream) {
+    UTTT_CHECK(n >= 0 && n_children >= 1 && n_children <= 81 && alpha > 0.0f && (n == 0 || out_dev), "bad argument");
+    UTTT_CUDA_OK(launch_dirichlet(seed, game0, n, n_children, alpha, out_dev, (cudaStream_t)stream));
+    return 0;
+}
+
 int uttt_set_progress_callback(uttt_engine* e, uttt_progress_fn fn, void* user) {
     UTTT_CHECK(e != nullptr, "null engine");
     e->progress_cb = fn;

@@ -41,6 +41,25 @@ __device__ float gamma_sample(float alpha, uint32_t seed, uint64_t game, uint32_
     return g;
 }
 
+// diagnostics (uttt_debug_dirichlet): the root-noise sampler on its own -- out[g][a] = Dirichlet(alpha) over n_children
+// children for game game0 + g at ply 0, exactly the draw tp_expand mixes into the root priors
+__global__ void __launch_bounds__(128) dirichlet_kernel(uint32_t seed, uint64_t game0, int64_t n, int n_children, float alpha,
+                                                        float* __restrict__ out) {
+    const int64_t g = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (g >= n) return;
+    float v[3] = {0.f, 0.f, 0.f}, sum = 0.0f;
+    for (int q = 0, a = lane; a < n_children; a += 32, q++) { v[q] = gamma_sample(alpha, seed, game0 + (uint64_t)g, 0u, (uint32_t)a); sum += v[q]; }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(FULL, sum, off);
+    for (int q = 0, a = lane; a < n_children; a += 32, q++) out[g * n_children + a] = sum > 0.0f ? v[q] / sum : 1.0f / (float)n_children;
+}
+cudaError_t launch_dirichlet(uint32_t seed, uint64_t game0, int64_t n, int n_children, float alpha, float* out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    dirichlet_kernel<<<(unsigned)((n + 3) / 4), 128, 0, s>>>(seed, game0, n, n_children, alpha, out);
+    return cudaGetLastError();
+}
+
 struct TpAux {                 // per tree, per pending leaf
     int32_t path_len[TP_MAX_LEAVES];
     int32_t nn_row[TP_MAX_LEAVES];

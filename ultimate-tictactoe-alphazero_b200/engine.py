@@ -80,6 +80,7 @@ ABI = {
     "uttt_set_root_noise": ([_vp, C.c_float, C.c_float], C.c_int),
     "uttt_set_selfplay_temperature": ([_vp, C.c_float], C.c_int),
     "uttt_set_progress_callback": ([_vp, _vp, _vp], C.c_int),
+    "uttt_debug_dirichlet": ([C.c_uint32, C.c_uint64, C.c_int64, C.c_int32, C.c_float, _vp, _vp], C.c_int),
     "uttt_mcts_begin": ([_vp, _vp, C.c_int32, C.c_int32, C.c_int32], C.c_int),
     "uttt_mcts_advance": ([_vp, C.POINTER(C.c_int32)], C.c_int),
     "uttt_mcts_get_leaves": ([_vp, _vp, _vp, _vp], C.c_int),
@@ -191,6 +192,14 @@ def game_playout(seed, game0, n, device="cuda", stream=None):
     rs = torch.empty((n,), dtype=torch.int32, device=device)
     _check(load_library().uttt_game_playout(seed, game0, n, _ptr(dg), _ptr(pl), _ptr(rs), _stream(stream)))
     return dg, pl, rs
+
+
+def dirichlet_samples(seed, game0, n, n_children, alpha, device="cuda", stream=None):
+    """(n, n_children) float32: the root-noise draws of games game0 .. game0 + n - 1 at ply 0 (diagnostics)"""
+    import torch
+    out = torch.empty((n, n_children), dtype=torch.float32, device=device)
+    _check(load_library().uttt_debug_dirichlet(seed, game0, n, n_children, float(alpha), _ptr(out), _stream(stream)))
+    return out
 
 
 # ------------------------------------------------------------------------------------ weights
