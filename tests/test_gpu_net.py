@@ -315,8 +315,8 @@ def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
     """The trunk kernel is chosen on the device from the batch size and the group sizes from ceil(n / pairs): every
     boundary of that dispatch must produce the same rows.  Default (UTTT_TRUNK=4, one launch that branches on the device,
     net_auto.cu): one group per CTA pair up to 370 positions (net_tc2), two groups in flight above (net_pp, cta_group::2).  All of them accumulate a row in the
-    same order -- bit-identical -- except the one-tile group of the 6/7-positions-per-pair case (371..518 positions),
-    whose K loop is split over two accumulators: fp32 re-association, checked on a well-conditioned network."""
+    same order: bit-identical rows -- including the one-tile group of the 6/7-positions-per-pair case (371..518
+    positions), whose weight stages are issued by two threads in turn into one accumulator."""
     import copy
     import engine
     e, model, sts = setup
@@ -324,7 +324,7 @@ def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
     damped = _damped(copy.deepcopy(model))
     e3 = engine.Engine(n_slots=1600, max_sims=50, max_batch=8, max_games=8)
     try:
-        for net, tol in ((model, None), (damped, TOL)):     # TOL = 1e-2, the bar of the bf16 path against fp32
+        for net in (model, damped):
             e3.upload_model(net)
             ref_p, ref_v = _forward(e3, big[:370], engine.EVAL_NET_BF16)     # one group per pair
             big_p, big_v = _forward(e3, big, engine.EVAL_NET_BF16)           # 3 super-groups of 2 x 5 positions on some pairs
@@ -332,16 +332,7 @@ def test_trunk_variant_boundaries_give_identical_rows(setup, monkeypatch):
             for n in (1, 2, 3, 73, 74, 75, 147, 148, 149, 221, 222, 223, 295, 296, 297, 369, 370, 371, 372, 443, 444, 445,
                       500, 517, 518, 519, 520, 591, 592, 593, 665, 666, 667, 739, 740, 741, 800, 1111, 1480, 1481):
                 p, v = _forward(e3, big[:n], engine.EVAL_NET_BF16)
-                if 370 < n <= 518:
-                    ptot = -(-n // 74)
-                    split = (np.arange(n) % ptot) >= 5                        # positions of the one-tile group
-                    assert (p[~split] == big_p[:n][~split]).all() and (v[~split] == big_v[:n][~split]).all(), n
-                    if tol is None:      # random init: logits up to +-400, any rounding difference can flip a near tie
-                        assert (p[split].argmax(1) == big_p[:n][split].argmax(1)).mean() > 0.9, n
-                    else:
-                        assert np.abs(p - big_p[:n]).max() < tol and np.abs(v - big_v[:n]).max() < tol, n
-                else:
-                    assert (p == big_p[:n]).all() and (v == big_v[:n]).all(), n
+                assert (p == big_p[:n]).all() and (v == big_v[:n]).all(), n
         e3.upload_model(model)
         ref_p, ref_v = _forward(e3, big[:800], engine.EVAL_NET_BF16)
         f32_p, _ = _forward(e3, big[:64], engine.EVAL_NET_FP32)

@@ -70,7 +70,9 @@ def _search_and_replay(e, roots, sims, batch, evaluator, exact_rows, temperature
 @pytest.mark.parametrize("n_roots", [60, 148, 300, 370, 450, 518])
 def test_slot_mode_search_replays_bit_exactly_in_every_band(nets, n_roots):
     """UTTT_EVAL_NET_BF16 with up to 518 trees = slot mode + trunk_auto_kernel + fused heads (the benchmarked path):
-    <= 148 (one tile per CTA), 149-370 (two tiles), 371-518 (two groups in flight, cta_group::2, split-K one-tile group)"""
+    <= 148 (one tile per CTA), 149-370 (two tiles), 371-518 (two groups in flight, cta_group::2 MMAs; the one-tile group's
+    weight stages issued by two threads in turn).  The recorded rows equal a stand-alone forward of the same leaves bit for
+    bit in every band: a row's arithmetic does not depend on the batch it was evaluated in."""
     import engine
     model, damped = nets
     roots = _roots(n_roots)
@@ -78,20 +80,12 @@ def test_slot_mode_search_replays_bit_exactly_in_every_band(nets, n_roots):
     try:
         e.upload_model(model)
         hist0 = e.batch_histogram()
-        same, *_ = _search_and_replay(e, roots, 50, 8, engine.EVAL_NET_BF16, exact_rows=n_roots <= 370)
+        _search_and_replay(e, roots, 50, 8, engine.EVAL_NET_BF16, exact_rows=True)
         hist = e.batch_histogram()
         assert hist[(n_roots - 1) >> 4] + hist[min(63, n_roots >> 4)] > 0, hist      # the band did occur
-        if n_roots > 370:
-            # the one-tile group of the 371..518 band accumulates split K (other bits than a stand-alone forward; a
-            # different fp32 sum can round an activation to the neighbouring bf16 value, so two bf16 evaluations of one
-            # position differ by up to the bf16 error itself, ~1e-2 in the value): those rows are checked on a
-            # well-conditioned network, where that noise stays far below the difference between two positions
-            assert same.mean() > 0.5
+        if n_roots > 370:          # the band whose one-tile group is issued by two threads in turn, on a second network
             e.upload_model(damped)
-            same, p2, pol, v2, val = _search_and_replay(e, roots, 50, 8, engine.EVAL_NET_BF16, exact_rows=False)
-            assert same.mean() > 0.5 and np.abs(p2 - pol).max() < 1e-3 and np.abs(v2 - val).max() < 3e-2
-            wrong = np.roll(np.arange(len(val)), 1)                # what a row handed to the wrong tree would look like
-            assert np.median(np.abs(p2[wrong] - pol).max(1)) > 5 * np.abs(p2 - pol).max()
+            _search_and_replay(e, roots, 50, 8, engine.EVAL_NET_BF16, exact_rows=True)
         # other search shapes of the same path
         for sims, batch, T in ((50, 1, 1.0), (37, 5, 0.0), (10, 2, 1.0)):
             _search_and_replay(e, roots[: min(n_roots, 96)], sims, batch, engine.EVAL_NET_BF16, exact_rows=False, temperature=T)

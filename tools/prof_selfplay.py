@@ -22,7 +22,7 @@ torch.manual_seed(0)
 e = engine.Engine(n_slots=min(a.games, a.slots), max_sims=a.sims, max_batch=a.batch, max_games=a.games)
 e.upload_model(DualNetwork().eval())
 e.set_profile_level(int(os.environ.get("UTTT_PROFILE", "2")))
-ev = engine.EVAL_NET_FP32 if a.numerics == "fp32" else engine.EVAL_NET_BF16
+ev = engine.evaluator_of(a.numerics)
 for r in range(a.reps):
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -49,9 +49,9 @@ def launches():
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, "%s_launches.md" % tag), "w") as f:
         f.write("# ncu launch list, round %s\n\n" % tag)
-        f.write("`ncu --metrics gpu__time_duration.sum --clock-control none -s 300 -c 700 python tools/prof_selfplay.py --games 500`\n")
-        f.write("(C3 workload: 500 games, 50 sims/move, batch 8; launches 300..999 of one self-play cycle (two launches per round); per-launch\n"
-                "times are cold-cache and serialised -- compare SHARES, not absolutes)\n\n")
+        f.write(open(os.path.join(G, "launches_%s.cmd" % tag)).read() if os.path.exists(os.path.join(G, "launches_%s.cmd" % tag)) else "")
+        f.write("\n(C3 workload: 500 games, 50 sims/move, batch 8, two launches per round; per-launch times are cold-cache and\n"
+                "serialised -- compare SHARES, not absolutes)\n\n")
         f.write("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("| %s | %d | %.1f | %.2f | %.1f%% |\n" % (k, v[0], v[1] / 1e3, v[1] / 1e3 / v[0], 100 * v[1] / tot))
@@ -84,9 +84,8 @@ def full(name):
 
 
 launches()
-full("trunk1")     # trunk_tc_kernel     (one CTA per group; batch of 740 positions; UTTT_TRUNK=1/2 only)
 full("trunk2")     # trunk_auto_kernel -> trunk_tc2_body<2> (CTA pair per group, 2 tiles per CTA; batch of 345 positions)
-full("trunk3")     # trunk_tc2_kernel<3> (CTA pair per group, 3 tiles per CTA; batch of 500 positions; UTTT_TRUNK=2 only)
+full("trunkx3")    # trunk_x3_kernel (split-bf16: 3 MMAs per K-block; batch of 500 positions = groups of 5 + 2 per CTA pair)
 full("trunkpp")    # trunk_auto_kernel, launch 200 of a 500-game cycle (slot mode, ~495 positions): trunk_pp_body<1> (two groups in
                    # flight, cta_group::2) + heads FC tail
 full("heads")      # heads_fc_kernel (standalone form of the heads' FC layers; 500 positions, warm L2)

@@ -31,6 +31,27 @@ void set_error(const char* fmt, ...);
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Programmatic dependent launch (the round loop is tree_round -> trunk -> tree_round -> ...: each kernel needs the previous
+// one's output from its first instruction, but its blocks can be scheduled and resident while the previous kernel drains,
+// which hides the launch latency of the boundary).  A kernel launched through launch_pdl may start before its predecessor
+// in the stream has finished: it must execute pdl_wait() before touching anything the predecessor writes, and may call
+// pdl_trigger() to let its own successor be scheduled early.  UTTT_PDL=0 turns the attribute off (plain stream order).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---------------------------------------------------------------- network geometry
 constexpr int NET_C = 128;        // DN_FILTERS          dual_network.py:12
 constexpr int NET_BLOCKS = 16;    // DN_RESIDUAL_NUM     dual_network.py:13
@@ -138,6 +159,9 @@ struct NetWeights {
     __nv_bfloat16* res_w_2sm;        // [32*9 stages][2][8 blocks]...
     __nv_bfloat16* conv_in_w_2sm;    // [2 stages][2][8 taps]... (16 tap slots, 9 used)
     __nv_bfloat16* bias_blk_2sm;     // [33][2][1 block]...
+    // the 7-positions-per-pair instantiation (the 500-game cycle's batches) streams a quarter of a layer per stage
+    __nv_bfloat16* res_w_2sm18;      // [32*4 stages][2][18 blocks]...
+    __nv_bfloat16* conv_in_w_2sm18;  // [1 stage][2][18 tap slots (9 used)]...
     // split-bf16 ("bf16x3") copies for trunk_x3_kernel: every block is followed by its lo part, lo = bf16(w - hi)
     __nv_bfloat16* res_w_x3;         // [32][72 K-blocks][hi, lo][2 k-panels][128][8]
     __nv_bfloat16* conv_in_w_x3;     // [9 taps][hi, lo][2][128][8]

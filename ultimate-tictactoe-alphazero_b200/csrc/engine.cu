@@ -369,7 +369,7 @@ int uttt_destroy(uttt_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
-    float* wp[] = {(float*)e->w.res_w_x3, (float*)e->w.conv_in_w_x3, (float*)e->w.bias_blk_x3, e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, e->w.head_w, e->w.pol_conv_w,
+    float* wp[] = {(float*)e->w.res_w_x3, (float*)e->w.conv_in_w_x3, (float*)e->w.bias_blk_x3, e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, (float*)e->w.res_w_2sm18, (float*)e->w.conv_in_w_2sm18, e->w.head_w, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b, e->w.heads_pack};
     for (float* p : wp) if (p) cudaFree(p);
@@ -554,6 +554,13 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
         UTTT_CUDA_OK(launch_split_weights_2sm(W.res_w_bf16, W.res_w_2sm, 32 * 72, 8, e->stream));
         UTTT_CUDA_OK(launch_split_weights_2sm(W.conv_in_w_bf16, W.conv_in_w_2sm, 12, 8, e->stream));
         UTTT_CUDA_OK(launch_split_weights_2sm(W.bias_blk, W.bias_blk_2sm, 33, 1, e->stream));
+        if (!W.res_w_2sm18) UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_2sm18, (size_t)32 * 72 * blk * sizeof(__nv_bfloat16)));
+        if (!W.conv_in_w_2sm18) {
+            UTTT_CUDA_OK(cudaMalloc((void**)&W.conv_in_w_2sm18, (size_t)18 * blk * sizeof(__nv_bfloat16)));
+            UTTT_CUDA_OK(cudaMemset(W.conv_in_w_2sm18, 0, (size_t)18 * blk * sizeof(__nv_bfloat16)));
+        }
+        UTTT_CUDA_OK(launch_split_weights_2sm(W.res_w_bf16, W.res_w_2sm18, 32 * 72, 18, e->stream));
+        UTTT_CUDA_OK(launch_split_weights_2sm(W.conv_in_w_bf16, W.conv_in_w_2sm18, 12, 18, e->stream));
     }
     {
         std::vector<float> hw(387);

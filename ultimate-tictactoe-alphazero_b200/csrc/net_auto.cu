@@ -58,12 +58,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(pp::THREADS, 1)
 trunk_auto_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wq_in,
                   const __nv_bfloat16* __restrict__ wq_bias,                      // cta_group::1 packing (net_tc2)
                   const __nv_bfloat16* __restrict__ wq2, const __nv_bfloat16* __restrict__ wq2_in,
-                  const __nv_bfloat16* __restrict__ wq2_bias,                     // per-CTA halves (net_pp)
+                  const __nv_bfloat16* __restrict__ wq2_bias,                     // per-CTA halves, 18-block stages (net_pp<1>)
                   const __nv_bfloat16* __restrict__ planes, const float* __restrict__ headw, float* headfeat, uint4* skip,
                   const int32_t* __restrict__ count, int small_cap, int max_count, long long* dbg,
                   HeadsFC fc, float* policy, float* value /* null: the heads' FC layers are a separate kernel */,
                   const uint8_t* __restrict__ slot_flags, int n_slots /* slot mode (needs the fused heads), else null */) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    pdl_trigger();          // the next round's tree kernel may be scheduled (it waits for this grid's policy / value rows)
+    pdl_wait();             // this round's tree kernel has finished: slot flags / queue length and planes are visible
     const bool stamp = dbg && blockIdx.x == 0 && threadIdx.x == 0;          // diagnostics: phases of CTA 0
     if (stamp) dbg[200] = clock64();
     const int n_pairs = (int)gridDim.x >> 1, pair = (int)blockIdx.x >> 1;
@@ -117,11 +119,9 @@ cudaError_t launch_trunk_auto(const NetWeights& w, const __nv_bfloat16* planes, 
     const int cap1 = (n_sm / 2) * (pp::Cfg<1>::MAX_PA + pp::Cfg<1>::MAX_PB);
     if (policy && max_rows > cap1) return cudaErrorInvalidValue;
     if (slot_flags && (!policy || n_slots > 32 * SLOT_CHUNKS || n_slots > max_rows)) return cudaErrorInvalidValue;
-    trunk_auto_kernel<<<2 * pairs, pp::THREADS, AUTO_SMEM_TOTAL, s>>>(w.res_w_bf16, w.conv_in_w_bf16, w.bias_blk, w.res_w_2sm,
-                                                                      w.conv_in_w_2sm, w.bias_blk_2sm, planes, w.head_w, headfeat,
-                                                                      reinterpret_cast<uint4*>(skip), count, small_cap, cap1, dbg,
-                                                                      heads_fc_of(w), policy, value, slot_flags, n_slots);
-    return cudaGetLastError();
+    return launch_pdl(trunk_auto_kernel, dim3(2 * pairs), dim3(pp::THREADS), AUTO_SMEM_TOTAL, s, w.res_w_bf16, w.conv_in_w_bf16,
+                      w.bias_blk, w.res_w_2sm18, w.conv_in_w_2sm18, w.bias_blk_2sm, planes, w.head_w, headfeat,
+                      reinterpret_cast<uint4*>(skip), count, small_cap, cap1, dbg, heads_fc_of(w), policy, value, slot_flags, n_slots);
 }
 
 }  // namespace uttt

@@ -53,7 +53,7 @@ cudaError_t launch_trunk_pp(const NetWeights& w, const __nv_bfloat16* planes, fl
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
     const int cap1 = (n_sm / 2) * (pp::Cfg<1>::MAX_PA + pp::Cfg<1>::MAX_PB);
     pp::trunk_pp_kernel<1><<<2 * pairs, pp::THREADS, pp::Cfg<1>::SMEM_BYTES, s>>>(
-        w.res_w_2sm, w.conv_in_w_2sm, w.bias_blk_2sm, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, min_count,
+        w.res_w_2sm18, w.conv_in_w_2sm18, w.bias_blk_2sm, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, min_count,
         cap1, dbg);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess || max_rows <= cap1) return e;

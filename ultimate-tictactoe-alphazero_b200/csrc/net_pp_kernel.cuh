@@ -9,9 +9,9 @@
 //      epilogue    :              epi(A, L)   epi(B, L)     epi(A, L+1)  ...
 //
 // so a layer's epilogue always has the other group's MMAs to hide behind.  Group A holds 5 positions (2 + 2 accumulator
-// tiles), group B the rest of the pair's share (instantiation 1: up to 2 positions = 1 + 1 tiles and a 6-stage weight
-// ring, instantiation 2: up to 5 positions and 4 stages).  Rows are bit-identical to net_tc2_kernel.cuh except group B of
-// instantiation 1 (split K: two partial accumulators added in the epilogue).
+// tiles), group B the rest of the pair's share (instantiation 1: up to 2 positions = 1 + 1 tiles, weight stages of a
+// quarter layer; instantiation 2: up to 5 positions, stages of 8 K-blocks).  Rows are bit-identical to net_tc2_kernel.cuh: every accumulator
+// sums its K-blocks in the order of tcx::kblock_of, whichever kernel and thread issued them.
 //
 // The MMAs are cta_group::2 pair MMAs (M = 256: tile t of the leader CTA and tile t of its peer, N = 128) issued by the
 // leader CTA only; the B operand is split by output channel between the two CTAs, so each CTA streams and stores HALF of
@@ -38,11 +38,6 @@ constexpr int POS_ROWS = 100;
 constexpr int LEAD = 11;
 constexpr int LT = 2;                           // accumulator tiles per CTA of group A (and the number of issuer warps)
 constexpr int NG = 2;                           // groups in flight
-constexpr int STAGE_BLOCKS = 8;                 // K-blocks (MMAs per tile pair) per weight stage: the issuer threads pay one
-                                                // barrier wait and one commit (200+ cycles each) per stage
-constexpr int STAGE_BYTES = STAGE_BLOCKS * 2048; // per CTA: its output-channel half of the stage's K-blocks
-constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
-constexpr int IN_STAGES = 2;                    // conv_input: 16 tap slots (9 used)
 constexpr int BIAS_BYTES = 2048;                // per CTA
 constexpr int CONST_BYTES = 4096;
 constexpr int EPI_WARPS = 8 * LT;
@@ -61,7 +56,18 @@ struct Cfg {
     static constexpr int A_BYTES = 16 * PANEL_A, B_BYTES = 16 * PANEL_B;            // 16 channel panels per group
     static constexpr int CONST_OFF = A_BYTES + B_BYTES;   // [2][128][8] bf16: rows (1,1,0,...,0), the A operand of the bias MMA
     static constexpr int W_OFF = CONST_OFF + CONST_BYTES;
-    static constexpr int STAGES = (LTB == 1) ? 6 : 4;
+    // K-blocks (MMAs per tile pair) per weight stage: an issuer thread pays one barrier wait and one commit per stage,
+    // 200+ cycles each while the tensor pipe saturates shared memory.  LTB = 1: group B is ONE tile pair, whose 72 MMAs
+    // of a layer must be issued at 64 cycles each by one thread -- with a quarter of a layer (18 K-blocks, 36 KiB per CTA)
+    // per stage that thread has 1152 cycles per stage for its two barrier operations and 18 MMA issues.  (Round 1 split
+    // that tile's K loop over two threads and two accumulators instead: same speed, but other low bits than every other
+    // batch band; handing one accumulator to and fro between two threads with tcgen05 fences is bit-identical but the
+    // hand-over sits on the issue path: +3 % per cycle.)
+    static constexpr int STAGE_BLOCKS = (LTB == 1) ? 18 : 8;
+    static constexpr int STAGE_BYTES = STAGE_BLOCKS * 2048;       // per CTA: its output-channel half of the stage's K-blocks
+    static constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
+    static constexpr int IN_STAGES = (LTB == 1) ? 1 : 2;          // conv_input: 16 / 18 tap slots (9 used)
+    static constexpr int STAGES = (LTB == 1) ? 3 : 4;
     static constexpr int BAR_OFF = W_OFF + STAGES * STAGE_BYTES;
     static constexpr int HEAD_OFF = BAR_OFF + 512;        // [128*LT rows][4] floats: head partial sums
     static constexpr int SMEM_BYTES = HEAD_OFF + 128 * LT * 16;
@@ -100,8 +106,8 @@ __host__ __device__ inline int pair_positions(int n_pos, int n_pairs) {
 
 // the kernel body (see net_tc2_kernel.cuh); __global__ wrappers in net_pp.cu, device-side dispatch in net_auto.cu
 template <int LTB>
-__device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ wq,        // [32*9 stages][2 ranks][8 K-blocks][2][64][8] bf16
-                const __nv_bfloat16* __restrict__ wq_in,     // conv_input: [2 stages][2 ranks][8 taps][2][64][8] bf16
+__device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ wq,        // [32 * STAGES_PER_LAYER stages][2 ranks][STAGE_BLOCKS K-blocks][2][64][8] bf16
+                const __nv_bfloat16* __restrict__ wq_in,     // conv_input: [IN_STAGES][2 ranks][STAGE_BLOCKS tap slots][2][64][8] bf16
                 const __nv_bfloat16* __restrict__ wq_bias,   // [33][2 ranks][2][64][8] bf16: per layer the BN shift as a K=16 B block
                 const __nv_bfloat16* __restrict__ planes,    // network input [rows][3][81] bf16
                 const float* __restrict__ headw,             // [3][128] policy conv (2) + value conv; [384..386] shifts
@@ -113,7 +119,9 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
                 int n_pos_known = -1,                        // >= 0: the batch size (slot mode, see net_auto.cu)
                 const int* src_rows = nullptr) {             // slot mode: position i of this pair reads planes row src_rows[i]
     using C = Cfg<LTB>;
-    constexpr int STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, HEAD_OFF = C::HEAD_OFF, CONST_OFF = C::CONST_OFF;
+    constexpr int STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, HEAD_OFF = C::HEAD_OFF, CONST_OFF = C::CONST_OFF,
+                  STAGE_BLOCKS = C::STAGE_BLOCKS, STAGE_BYTES = C::STAGE_BYTES, STAGES_PER_LAYER = C::STAGES_PER_LAYER,
+                  IN_STAGES = C::IN_STAGES;
     constexpr int MAX_P = C::MAX_PA;
     extern __shared__ __align__(1024) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,11 +155,6 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
     auto bar_act = [&](int g, int t) { return bar_grp + 8u * (uint32_t)(g * GRP_BARS + LT + t); };
     static_assert(16 * STAGES + 8 * NG * GRP_BARS + 4 <= 512, "barrier block");
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + BAR_OFF + 16 * STAGES + 8 * NG * GRP_BARS);
-    // group B of the 7-positions instantiation has one tile pair: its K loop is split between the two issuer threads
-    // (even / odd weight stages) into two accumulators that the epilogue adds, because one thread cannot issue
-    // 64-cycle MMAs fast enough (every shared-memory barrier operation of the issuer takes 200+ cycles while the tensor
-    // pipe saturates shared memory: measured ~107 cycles per MMA and thread)
-    auto split_k = [&](int g) { return LTB == 1 && g == 1; };
     const int bnd_quarter = (rank == 0) ? 3 : 0;              // the quarter-warp that owns the rows next to the peer
 
     if (threadIdx.x == 0) {
@@ -161,7 +164,7 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
         }
         for (int g = 0; g < NG; g++) {
             for (int t = 0; t < LT; t++) {
-                mbar_init(bar_accum(g, t), split_k(g) ? 2 : 1);
+                mbar_init(bar_accum(g, t), 1);
                 // own 8 epilogue warps + the 2 boundary warps of each row neighbour (the peer's halo rows arrive as
                 // transaction bytes) + on the leader the peer's forwarded arrive for its tile of the same index
                 mbar_init(bar_act(g, t), 8 + (t > 0 ? 2 : 0) + (t < geo[g].tiles - 1 ? 2 : 0) + ((rank == 0 && t < geo[g].T1) ? 1 : 0));
@@ -282,7 +285,6 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
                 if (r.bnd) mbar_wait_spin<false>(bar_accum(g, (rank == 0) ? 0 : geo[g].T0 - 1), lpar);
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0 && layer < 16) dbg[(16 * g + layer) * 4 + 2] = clock64();
                 tc_fence_after();
-                const bool dual = split_k(g) && layer >= 0;         // two partial accumulators (columns +128): add them
                 float va[16], vb[16];
                 float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
                 tmem_ld16(taddr, va);
@@ -291,12 +293,6 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
                     float* v = (ch & 1) ? vb : va;
                     float* o = (ch & 1) ? va : vb;
                     tmem_ld_wait();
-                    if (dual) {
-                        tmem_ld16(taddr + 128u + (uint32_t)(ch * 16), o);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; j++) v[j] += o[j];
-                    }
                     if (ch < 3) tmem_ld16(taddr + (uint32_t)((ch + 1) * 16), o);
                     f16x8_add2(sk[2 * ch], v);
                     f16x8_add2(sk[2 * ch + 1], v + 8);
@@ -454,18 +450,17 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
                 if (++stage == STAGES) { stage = 0; par ^= 1u; }
             };
             // per group, fixed for the kernel: does this thread issue for it, into which accumulator, from which rows
-            bool g_stream[NG], g_issue[NG], g_split[NG];
+            bool g_stream[NG], g_issue[NG];
             uint32_t g_tmem[NG], g_act[NG], g_accum[NG];
             uint64_t g_adesc[NG];
             int g_panel16[NG];
 #pragma unroll
             for (int g = 0; g < NG; g++) {
                 const Geo& G = geo[g];
-                g_split[g] = split_k(g);
-                const int tile = g_split[g] ? 0 : lt;           // split K: both issuers work on tile pair 0
+                const int tile = lt;
                 g_stream[g] = G.T0 > 0;
                 g_issue[g] = tile < G.T0;
-                g_tmem[g] = tmem_base + (uint32_t)((g * LT + (g_split[g] ? lt : tile)) * 128);
+                g_tmem[g] = tmem_base + (uint32_t)((g * LT + tile) * 128);
                 g_act[g] = bar_act(g, tile);
                 g_accum[g] = bar_accum(g, tile);
                 g_panel16[g] = (int)(grp_panel(g) / 16);
@@ -478,7 +473,6 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
                 for (int g = 0; g < NG; g++) {
                     if (!g_stream[g]) continue;                     // the pair does not have this group
                     const bool mine = g_issue[g];                   // otherwise: walk and release the stages only
-                    const bool split = g_split[g];
                     const uint32_t tmem_d = g_tmem[g];
                     const uint64_t a_desc = g_adesc[g];
                     const int panel16 = g_panel16[g];
@@ -489,11 +483,9 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
                         tc_fence_after();
                     }
                     if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer >= 0 && layer < 16) dbg[(16 * g + layer) * 4 + 0] = clock64();
-                    // accumulator := BN shift (constant rows x bias block); starts the layer's accumulation (split K: in the
-                    // first thread's accumulator; conv_input is not split)
-                    const bool first = !split || lt == 0;
+                    // accumulator := BN shift (constant rows x bias block); starts the layer's accumulation
                     next_stage();
-                    if (mine && first && leader) umma_bf16_2sm(tmem_d, bias_a, b_st, IDESC, 0u);
+                    if (mine && leader) umma_bf16_2sm(tmem_d, bias_a, b_st, IDESC, 0u);
                     if (leader) release_stage();
                     advance();
                     if (layer < 0) {
@@ -501,7 +493,7 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
 #pragma unroll
                         for (int s = 0; s < IN_STAGES; s++) {
                             next_stage();
-                            if (mine && first && leader) {
+                            if (mine && leader) {
 #pragma unroll
                                 for (int j = 0; j < STAGE_BLOCKS; j++) {
                                     const int tap = STAGE_BLOCKS * s + j;
@@ -517,18 +509,16 @@ __device__ __forceinline__ void trunk_pp_body(const __nv_bfloat16* __restrict__ 
                             advance();
                         }
                     } else {
-                        // stage s holds K-blocks 8s .. 8s+7 in the order of tcx::kblock_of; split K: even stages belong to
-                        // issuer 0, odd stages to issuer 1 (whose first MMA of the layer overwrites its accumulator)
+                        // stage s holds K-blocks STAGE_BLOCKS * s ... in the order of tcx::kblock_of
 #pragma unroll
                         for (int s = 0; s < STAGES_PER_LAYER; s++) {
                             next_stage();
-                            if (mine && leader && (!split || (s & 1) == lt)) {
+                            if (mine && leader) {
 #pragma unroll
                                 for (int ks = 0; ks < STAGE_BLOCKS; ks++) {
                                     const int m = STAGE_BLOCKS * s + ks, q = m / 18, rr = m % 18, tap = rr >> 1, unit = q + 4 * (rr & 1);
                                     const int off = (tap / 3 - 1) * 10 + (tap % 3 - 1) + 2 * unit * panel16;
-                                    umma_bf16_2sm(tmem_d, a_desc + (uint64_t)(int64_t)off, b_st + (uint64_t)(ks * 128), IDESC,
-                                                  (split && s == 1 && ks == 0) ? 0u : 1u);
+                                    umma_bf16_2sm(tmem_d, a_desc + (uint64_t)(int64_t)off, b_st + (uint64_t)(ks * 128), IDESC, 1u);
                                 }
                             }
                             if (leader) {

@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_begin_kernel(TreePa
 }
 
 __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreeParams P) {
+    pdl_trigger();          // the evaluator kernel behind this one may be scheduled now (it waits for this grid's results)
+    pdl_wait();             // the previous round's evaluator has finished: policy / value rows are visible
     int t = blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     // the other parity's counter was consumed by the previous round's evaluator: reset it
@@ -477,8 +479,7 @@ cudaError_t launch_tree_begin(const TreeParams& p, cudaStream_t s) {
     return cudaGetLastError();
 }
 cudaError_t launch_tree_round(const TreeParams& p, cudaStream_t s) {
-    tree_round_kernel<<<ceil_div(p.n_trees, WARPS_PER_BLOCK), 32 * WARPS_PER_BLOCK, 0, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(tree_round_kernel, dim3(ceil_div(p.n_trees, WARPS_PER_BLOCK)), dim3(32 * WARPS_PER_BLOCK), 0, s, p);
 }
 cudaError_t launch_hash_eval(const PackedState* states, const int32_t* k, const int32_t* count, int max_rows,
                              float* policy, float* value, int row_stride, int copy_stride, cudaStream_t s) {
