@@ -477,12 +477,12 @@ def main():
             "roofline": {"bound": "tensor", "kernel": kernel,
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of trunk_auto_kernel at a
-                         # batch of 500 positions (profiles/r1_trunkpp_full.md): weights 9.4 MB (+ the per-CTA-half copy),
-                         # planes, head features, policy / value rows; activations and the skip connection never reach DRAM
-                         "traffic": 15.18e6 if args.numerics == "bf16" else None,
-                         "traffic_unit": "bytes per launch from a cold-cache ncu capture, 1.55x the 9.9 MB algorithmic (both weight "
-                                         "packings are read once); tensor-bound kernel: informational",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at a batch of ~500 positions
+                         # (profiles/r2_trunkpp_full.md, r2_trunkx3_full.md): weights (9.4 MB bf16, 18.9 MB split-bf16), planes, head
+                         # features, policy / value rows; activations and the skip connection never reach DRAM
+                         "traffic": {"bf16": 15.49e6, "bf16x3": 20.89e6}.get(args.numerics),
+                         "traffic_unit": "bytes per launch from a cold-cache ncu capture (bf16: 1.56x the 9.9 MB algorithmic -- the weights "
+                                         "come from DRAM once per capture, from L2 in steady state); tensor-bound kernel: informational",
                          "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                          "flop_per_launch": evals * TRUNK_FLOP_PER_POSITION / max(trunk_launches, 1),
                          "flop_convention": "useful (algorithmic) FLOPs: 764.4 MFLOP per evaluated position, SURVEY 8(d)"
