@@ -586,6 +586,18 @@ int orc_pv_mcts_scores_table(const orc_state *root, float temperature, int evalu
     return n;
 }
 
+/* the Python-semantics search fed recorded rows (the gating match's search with a network evaluator, replayed) */
+int orc_py_mcts_counts_table(const orc_state *root, int evaluate_count, int batch_size, int n_entries, const uint32_t *states,
+                             const float *policy, const float *value, int *counts_out, int *misses_out) {
+    table_ctx t = {n_entries, states, policy, value, (uint8_t *)calloc((size_t)(n_entries > 0 ? n_entries : 1), 1), 0};
+    int n = orc_py_mcts_counts(table_eval_cb, &t, root, evaluate_count, batch_size, counts_out);
+    int unused = 0;
+    for (int j = 0; j < n_entries; j++) unused += !t.used[j];
+    if (misses_out) *misses_out = t.misses + (unused << 16);
+    free(t.used);
+    return n;
+}
+
 /* the hash-evaluator search, recording every distinct evaluated leaf in order (pins the replay machinery on the CPU:
  * replaying the record must reproduce the scores) */
 typedef struct { int cap, n; uint32_t *states; float *policy; float *value; } record_ctx;

@@ -58,6 +58,8 @@ void     orc_hash_eval(const orc_state *s, float policy[81], float *value);
 /* evaluator callback: fills policy[81], value for each of n states */
 /* pv_mcts.py:74-180 (the reference's pure-Python search): root visit counts in legal order; returns their number */
 int orc_py_mcts_counts_hash(const orc_state *root, int evaluate_count, int batch_size, int *counts_out);
+int orc_py_mcts_counts_table(const orc_state *root, int evaluate_count, int batch_size, int n_entries, const uint32_t *states,
+                             const float *policy, const float *value, int *counts_out, int *misses_out);
 int orc_pv_mcts_scores_table(const orc_state *root, float temperature, int evaluate_count, int batch_size, int n_entries,
                              const uint32_t *states, const float *policy, const float *value, float *scores_out,
                              int *counts_out, int *misses_out);

@@ -75,6 +75,8 @@ def oracle():
         L.orc_pv_mcts_scores_hash_record.restype = C.c_int
         L.orc_py_mcts_counts_hash.argtypes = [SP, C.c_int, C.c_int, i32p]
         L.orc_py_mcts_counts_hash.restype = C.c_int
+        L.orc_py_mcts_counts_table.argtypes = [SP, C.c_int, C.c_int, C.c_int, u32p, f32p, f32p, i32p, C.POINTER(C.c_int)]
+        L.orc_py_mcts_counts_table.restype = C.c_int
         L.orc_az_search_hash.argtypes = [SP, C.c_int, i32p]
         L.orc_az_search_hash.restype = C.c_int
         _oracle = L
@@ -211,6 +213,22 @@ def oracle_py_mcts(w, sims, batch):
     cn = np.zeros(81, np.int32)
     n = oracle().orc_py_mcts_counts_hash(C.byref(s), sims, batch, cn)
     return cn[:n].copy()
+
+
+def table_py_mcts(w, sims, batch, states, policy, value):
+    """the Python-semantics search (pv_mcts.py:74-180 restated, pinned by tests/golden/pymcts.npz) fed recorded rows
+    -> (root visit counts, leaves without a row, rows left unused)"""
+    states = np.ascontiguousarray(states, dtype=np.uint32).reshape(-1, 8)
+    policy = np.ascontiguousarray(policy, dtype=np.float32).reshape(-1, 81)
+    value = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)
+    n = len(value)
+    if n == 0:
+        states, policy, value = np.full((1, 8), 0xFFFFFFFF, np.uint32), np.zeros((1, 81), np.float32), np.zeros(1, np.float32)
+    s = state_from_packed(w)
+    cn = np.zeros(81, np.int32)
+    miss = C.c_int(0)
+    m = oracle().orc_py_mcts_counts_table(C.byref(s), sims, batch, n, states, policy, value, cn, C.byref(miss))
+    return cn[:m].copy(), miss.value & 0xFFFF, miss.value >> 16
 
 
 def oracle_az_search(w, sims):

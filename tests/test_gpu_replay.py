@@ -110,6 +110,36 @@ def test_compacted_queue_search_replays_bit_exactly(nets, n_roots, evaluator):
         e.close()
 
 
+@pytest.mark.parametrize("evaluator", ["bf16x3", "bf16"])
+def test_gating_search_with_network_replays_bit_exactly(nets, evaluator):
+    """the gating match's search (pv_mcts.py:74-180 semantics, UTTT_SP_PYSEARCH) with the NETWORK evaluator: the root is
+    evaluated too, so its row is part of the record; the C restatement of the Python search (pinned against the
+    unmodified reference module by tests/golden/pymcts.npz) fed the engine's own rows gives the same visit counts"""
+    import torch
+    import engine
+    model, _ = nets
+    ev = engine.evaluator_of(evaluator)
+    roots = _roots(200, seed=31)
+    e = engine.Engine(n_slots=200, max_sims=50, max_batch=8, max_games=8)
+    try:
+        e.upload_model(model)
+        e.trace(True)
+        _, counts, ns = e.mcts_search(roots, 50, 8, 1.0, ev, flags=engine.SP_PYSEARCH)
+        meta, st, pol, val = e.trace_read()
+        e.trace(False)
+        p2, v2 = e.net_forward(torch.from_numpy(st.view(np.int32)).cuda(), ev)
+        assert (p2.cpu().numpy() == pol).all() and (v2.cpu().numpy() == val).all()
+        groups = _by_key(meta, 0)
+        for i in range(len(roots)):
+            idx = groups[i]
+            assert (st[idx[0]] == roots[i]).all()                  # the first evaluated leaf of a tree is its root
+            got, miss, unused = O.table_py_mcts(roots[i], 50, 8, st[idx], pol[idx], val[idx])
+            assert miss == 0 and unused == 0 and len(got) == ns[i] and (got == counts[i, :ns[i]]).all(), i
+        assert (counts.sum(1) == 50 - 8).all()                     # the first flush backs up the root only (pv_mcts.py:150-165)
+    finally:
+        e.close()
+
+
 def test_full_selfplay_cycle_replays_bit_exactly(nets):
     """BASELINE config 3 as benchmarked (500 concurrent games, 50 simulations, batch 8, bf16 trunk, slot mode): every move
     of every game is searched again by the reference MCTS fed the rows the engine's network produced for that move's

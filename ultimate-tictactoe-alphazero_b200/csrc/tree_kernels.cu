@@ -351,13 +351,18 @@ __global__ void __launch_bounds__(32 * WARPS_PER_BLOCK) tree_round_kernel(TreePa
             if (lane + 32 < cnt) consider(c1, lane + 32);
             if (lane + 64 < cnt) consider(c2, lane + 64);
             for (int i = lane + 96; i < cnt; i += 32) consider(ch[i], i);
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {                 // first maximum wins (Q-M6)
-                float ob = __shfl_xor_sync(FULL, best, off);
-                int oi = __shfl_xor_sync(FULL, besti, off);
-                uint32_t ox = __shfl_xor_sync(FULL, bestx, off);
-                uint32_t ol = __shfl_xor_sync(FULL, bestlink, off);
-                if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; bestx = ox; bestlink = ol; }
+            // first maximum wins (Q-M6): the largest score by one warp reduction on an order-preserving integer image of
+            // the float (scores are never -0.0: q + u with u >= +0), then the smallest child index among the lanes that
+            // hold it, then that lane's node word -- 2 reductions + 2 shuffles instead of a 20-shuffle butterfly
+            {
+                const uint32_t fb = __float_as_uint(best);
+                const uint32_t key = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+                const uint32_t kmax = __reduce_max_sync(FULL, key);
+                besti = (int)__reduce_min_sync(FULL, key == kmax ? (uint32_t)besti : 0x7FFFFFFFu);
+                const int src = besti & 31;                          // child i is held by lane i % 32
+                // (a lane's own candidate is its FIRST maximum, so the winning lane's registers hold child besti)
+                bestx = __shfl_sync(FULL, bestx, src);
+                bestlink = __shfl_sync(FULL, bestlink, src);
             }
             node = (int)cbase + besti;
             link = bestlink;
