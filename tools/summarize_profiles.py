@@ -67,7 +67,7 @@ def full(name):
     hdr, units = rows[0], rows[1]
     with open(os.path.join(P, "%s_%s_full.md" % (tag, name)), "w") as f:
         f.write("# ncu --set full, %s kernel, round %s\n\n" % (name, tag))
-        f.write("`ncu --set full --clock-control none --import-source on -k regex:<kernel> ...` (commands: tools/gpu_round.sh)\n\n")
+        f.write("`ncu --set full --clock-control none --import-source on -k regex:<kernel> ...` (commands: tools/gpu_round2.sh)\n\n")
         seen = set()
         for r in rows[2:]:
             kname = r[hdr.index("Kernel Name")].split("(")[0]
