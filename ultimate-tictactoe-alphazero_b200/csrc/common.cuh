@@ -162,10 +162,14 @@ struct NetWeights {
     // the 7-positions-per-pair instantiation (the 500-game cycle's batches) streams a quarter of a layer per stage
     __nv_bfloat16* res_w_2sm18;      // [32*4 stages][2][18 blocks]...
     __nv_bfloat16* conv_in_w_2sm18;  // [1 stage][2][18 tap slots (9 used)]...
-    // split-bf16 ("bf16x3") copies for trunk_x3_kernel: every block is followed by its lo part, lo = bf16(w - hi)
+    // split-bf16 ("bf16x3") copies: every block is followed by its lo part, lo = bf16(w - hi) (staging for the split below)
     __nv_bfloat16* res_w_x3;         // [32][72 K-blocks][hi, lo][2 k-panels][128][8]
     __nv_bfloat16* conv_in_w_x3;     // [9 taps][hi, lo][2][128][8]
     __nv_bfloat16* bias_blk_x3;      // [33][2][128][8]: shift as three bf16 terms in k = 0, 1, 2
+    // ... and their per-CTA halves, what trunk_x3_kernel (cta_group::2 MMAs) streams: stages of 6 K-blocks
+    __nv_bfloat16* res_w_x3p;        // [32*12 stages][2 ranks][6 blocks][hi, lo][2 k-panels][64][8]
+    __nv_bfloat16* conv_in_w_x3p;    // [2 stages][2 ranks][6 tap slots (9 of 12 used)][hi, lo][2][64][8]
+    __nv_bfloat16* bias_blk_x3p;     // [33][2 ranks][2][64][8]
     float* head_w;                   // [3][128] policy conv (2 rows) + value conv, BN scale folded; [384..386] BN shifts
     // heads (fp32): policy conv [2][128] + shift[2], fc [81][162] + b; value conv [128] + shift, fc1 [256][81]+b, fc2 [256]+b
     float* pol_conv_w; float* pol_conv_b; float* pol_fc_w; float* pol_fc_b;
@@ -196,7 +200,9 @@ cudaError_t launch_trunk_tc2_small(const NetWeights& w, const __nv_bfloat16* pla
                                    int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg);
 int trunk_tc2_small_capacity(int n_sm);
 // two groups of positions per CTA pair in flight (net_pp.cu): batches of more than min_count positions
-cudaError_t launch_split_weights_2sm(const __nv_bfloat16* src, __nv_bfloat16* dst, int n_blocks, int blocks_per_stage, cudaStream_t s);
+// (subs = 16-byte-unit blocks per K-block: 1, or 2 for the split-bf16 arrays whose blocks are a hi and a lo part)
+cudaError_t launch_split_weights_2sm(const __nv_bfloat16* src, __nv_bfloat16* dst, int n_blocks, int blocks_per_stage, cudaStream_t s,
+                                     int subs = 1);
 cudaError_t launch_trunk_pp(const NetWeights& w, const __nv_bfloat16* planes, float* headfeat, const int32_t* count, int max_rows,
                             float* skip, int n_sm, cudaStream_t s, long long* dbg, int min_count);
 cudaError_t trunk_pp_init();

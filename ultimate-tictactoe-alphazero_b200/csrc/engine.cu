@@ -369,7 +369,7 @@ int uttt_destroy(uttt_engine* e) {
     cudaSetDevice(e->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : e->allocs) cudaFree(p);
-    float* wp[] = {(float*)e->w.res_w_x3, (float*)e->w.conv_in_w_x3, (float*)e->w.bias_blk_x3, e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, (float*)e->w.res_w_2sm18, (float*)e->w.conv_in_w_2sm18, e->w.head_w, e->w.pol_conv_w,
+    float* wp[] = {(float*)e->w.res_w_x3p, (float*)e->w.conv_in_w_x3p, (float*)e->w.bias_blk_x3p, (float*)e->w.res_w_x3, (float*)e->w.conv_in_w_x3, (float*)e->w.bias_blk_x3, e->w.conv_in_w, e->w.conv_in_b, e->w.res_w, e->w.res_b, (float*)e->w.res_w_bf16, (float*)e->w.conv_in_w_bf16, e->w.bias_all, (float*)e->w.bias_blk, (float*)e->w.res_w_2sm, (float*)e->w.conv_in_w_2sm, (float*)e->w.bias_blk_2sm, (float*)e->w.res_w_2sm18, (float*)e->w.conv_in_w_2sm18, e->w.head_w, e->w.pol_conv_w,
                    e->w.pol_conv_b, e->w.pol_fc_w, e->w.pol_fc_b, e->w.val_conv_w, e->w.val_conv_b, e->w.val_fc1_w,
                    e->w.val_fc1_b, e->w.val_fc2_w, e->w.val_fc2_b, e->w.heads_pack};
     for (float* p : wp) if (p) cudaFree(p);
@@ -542,6 +542,17 @@ static int upload_impl(uttt_engine* e, const uttt_weights* w, int on_device, con
                 }
             if (!W.bias_blk_x3) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_blk_x3, b3.size() * sizeof(__nv_bfloat16)));
             UTTT_CUDA_OK(cudaMemcpy(W.bias_blk_x3, b3.data(), b3.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+            // per-CTA halves for the cta_group::2 form (stages of 6 K-blocks; conv_input: 12 tap slots, 9 used)
+            const size_t blk3 = 2 * 2 * 128 * 8;
+            if (!W.res_w_x3p) UTTT_CUDA_OK(cudaMalloc((void**)&W.res_w_x3p, (size_t)32 * 72 * blk3 * sizeof(__nv_bfloat16)));
+            if (!W.conv_in_w_x3p) {
+                UTTT_CUDA_OK(cudaMalloc((void**)&W.conv_in_w_x3p, (size_t)12 * blk3 * sizeof(__nv_bfloat16)));
+                UTTT_CUDA_OK(cudaMemset(W.conv_in_w_x3p, 0, (size_t)12 * blk3 * sizeof(__nv_bfloat16)));
+            }
+            if (!W.bias_blk_x3p) UTTT_CUDA_OK(cudaMalloc((void**)&W.bias_blk_x3p, b3.size() * sizeof(__nv_bfloat16)));
+            UTTT_CUDA_OK(launch_split_weights_2sm(W.res_w_x3, W.res_w_x3p, 32 * 72, 6, e->stream, 2));
+            UTTT_CUDA_OK(launch_split_weights_2sm(W.conv_in_w_x3, W.conv_in_w_x3p, 9, 6, e->stream, 2));
+            UTTT_CUDA_OK(launch_split_weights_2sm(W.bias_blk_x3, W.bias_blk_x3p, 33, 1, e->stream));
         }
         // per-CTA halves of the three B-operand arrays for the cta_group::2 trunk
         const size_t blk = 2 * 128 * 8;
@@ -1034,6 +1045,11 @@ int uttt_debug_trunk_timeline(uttt_engine* e, int64_t* out128) {
         fprintf(stderr, "pp detail layer 20 (rel): A: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld | B: loop %lld act %lld pact %lld fence %lld stage %lld bias-issued %lld last-commit %lld\n",
                 0ll, d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0], d[5] - d[0], d[6] - d[0], d[8] - d[0], d[9] - d[0], d[10] - d[0], d[11] - d[0],
                 d[12] - d[0], d[13] - d[0], d[14] - d[0]);
+        // (the tc2 bodies use the same slots: epilogue thread 0 of layer 20 and the tile-0 issuer of layer 21)
+        fprintf(stderr, "tc2 detail, layer 20 -> 21 (cycles rel. accumulator observed by epilogue thread 0): last MMA of layer 20 committed %lld | "
+                "first chunk loaded %lld, stored %lld, fenced %lld, chunks published %lld %lld %lld %lld | issuer of tile 0 passed the "
+                "act barrier of quarter 0..3 at %lld %lld %lld %lld\n", d[12] - d[0], d[1] - d[0], d[2] - d[0], d[3] - d[0], d[4] - d[0],
+                d[5] - d[0], d[6] - d[0], d[7] - d[0], d[8] - d[0], d[9] - d[0], d[10] - d[0], d[11] - d[0]);
         long long au[10];
         UTTT_CUDA_OK(cudaMemcpy(au, e->tc_dbg + 200, sizeof(au), cudaMemcpyDeviceToHost));
         fprintf(stderr, "heads FC tail (cycles rel. body done): barriers ready %lld, features loaded %lld, chunk 0/1/2 landed %lld %lld %lld, "

@@ -25,8 +25,10 @@ trunk_tc2_kernel(const __nv_bfloat16* __restrict__ wq,
 // to 5 positions (2 + 2 accumulator tiles), each by one complete pass of the body (set-up and tear-down are ~1 % of a
 // pass here: every layer issues 3 x 72 MMAs per tile).  7 positions per pair -- the 500-game cycle -- cost 2 + 1 tile
 // times (groups of 5 and 2) instead of the 2 + 2 of two waves of 5-position groups over the whole grid.
-constexpr int X3_SMEM = Cfg<2, true>::SMEM_BYTES;
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<2, true>::THREADS, 1)
+// cta_group::2 MMAs, every CTA streams its output-channel half of the split weights (see Cfg: with cta_group::1 MMAs a
+// one-tile pass was 13 % slower -- 347 -> 301 us at up to 148 positions, 1035 -> 982 us at 500 -- with bit-identical rows).
+constexpr int X3_SMEM = Cfg<2, true, true>::SMEM_BYTES;
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<2, true, true>::THREADS, 1)
 trunk_x3_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __restrict__ wq_in,
                 const __nv_bfloat16* __restrict__ wq_bias, const __nv_bfloat16* __restrict__ planes,
                 const float* __restrict__ headw, float* headfeat, uint4* skip, const int32_t* __restrict__ count,
@@ -39,8 +41,8 @@ trunk_x3_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __res
     const int per_pair = (n_pos + n_pairs - 1) / n_pairs;
     const int first = pair * per_pair, last = min(n_pos, first + per_pair);
     for (int off = first; off < last; off += Cfg<2, true>::MAX_P)
-        trunk_tc2_body<2, true>(wq, wq_in, wq_bias, planes, headw, headfeat, skip, count, 0, 0x7FFFFFFF, off == first ? dbg : nullptr,
-                                min(Cfg<2, true>::MAX_P, last - off), nullptr, off, true);     // (dbg: timeline of the first pass)
+        trunk_tc2_body<2, true, true>(wq, wq_in, wq_bias, planes, headw, headfeat, skip, count, 0, 0x7FFFFFFF, off == first ? dbg : nullptr,
+                                      min(Cfg<2, true>::MAX_P, last - off), nullptr, off, true);     // (dbg: timeline of the first pass)
 }
 
 }  // namespace tc2
@@ -71,8 +73,8 @@ cudaError_t launch_trunk_x3(const NetWeights& w, const __nv_bfloat16* planes, fl
                             int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg) {
     int pairs = n_sm / 2;
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
-    tc2::trunk_x3_kernel<<<2 * pairs, tc2::Cfg<2, true>::THREADS, tc2::X3_SMEM, s>>>(
-        w.res_w_x3, w.conv_in_w_x3, w.bias_blk_x3, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, dbg);
+    tc2::trunk_x3_kernel<<<2 * pairs, tc2::Cfg<2, true, true>::THREADS, tc2::X3_SMEM, s>>>(
+        w.res_w_x3p, w.conv_in_w_x3p, w.bias_blk_x3p, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, dbg);
     return cudaGetLastError();
 }
 

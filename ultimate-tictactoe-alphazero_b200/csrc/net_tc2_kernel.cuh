@@ -40,7 +40,14 @@ constexpr uint32_t IDESC = tcx::IDESC_M128_N128_BF16;
 // connection is kept in fp32.  That is ~16 mantissa bits per operand: the mode that meets the reference's fp32 forward
 // (dual_network.py:89-121) within 1e-2 on random-init weights, at a third of the MMA rate.
 // Shared memory then holds 32 activation panels (16 hi + 16 lo) and a ring of 3 stages of 3 K-blocks (hi + lo = 8 KiB each).
-template <int LT, bool X3 = false>
+//
+// PAIR = the MMAs are cta_group::2 pair MMAs (M = 256: local tile t of the leader CTA and local tile t of its peer, issued by
+// the leader only, as in net_pp_kernel.cuh) and the B operand is split by output channel: each CTA streams and stores HALF
+// of every weight block.  Why: a cta_group::1 MMA of M = N = 128 reads 4 KiB of A and 4 KiB of B per 64 cycles = 128 B/clk,
+// all the shared-memory bandwidth of an SM, so the weight stream (one-tile groups of the split-bf16 mode: 590 KB per layer)
+// and the epilogue's stores slow the tensor pipe down (tools/micro/mma_shapes.cu); a pair MMA reads
+// 4 + 2 KiB per CTA.  Rows are bit-identical to the cta_group::1 form (same K-block order into the same accumulators).
+template <int LT, bool X3 = false, bool PAIR = false>
 struct Cfg {
     static_assert(LT == 2, "one instantiation: 2 tiles per CTA");
     static constexpr int LOC_TILES = LT;
@@ -49,15 +56,18 @@ struct Cfg {
     static constexpr int PANEL_BYTES = AROWS * 16;
     static constexpr int ACT_PANELS = X3 ? 32 : 16;        // channel panels [ci/8][row][8] bf16 (X3: panels 16.. hold the lo parts)
     static constexpr int A_BYTES = (ACT_PANELS + 2) * PANEL_BYTES;      // + the constant panel pair of the bias MMA
-    static constexpr int STAGES = X3 ? 3 : ((LT == 2) ? 4 : 3);
+    static constexpr int STAGES = X3 ? 3 : (PAIR ? 8 : 4);
     // K-blocks (one K = 16 slice of a layer: 1 MMA per tile, X3: 3) per weight stage.  An issuer thread pays one barrier
     // wait and one commit per stage (200+ cycles each while the tensor pipe saturates shared memory): with 4-block stages
     // a CTA that owns ONE tile (batches of up to 148 positions) was issue-bound at ~93 cycles per MMA
-    static constexpr int STAGE_BLOCKS = X3 ? 3 : 8;
-    static constexpr int BLOCK_BYTES = X3 ? 8192 : 4096;   // [2 k-panels][128 co][8] bf16 (X3: hi block, then lo block)
+    static constexpr int STAGE_BLOCKS = X3 ? (PAIR ? 6 : 3) : 8;
+    static constexpr int NCO = PAIR ? 64 : 128;            // output channels of the B operand held by this CTA
+    static constexpr int SUB_BYTES = 2 * NCO * 16;         // one [2 k-panels][NCO co][8] bf16 block
+    static constexpr int BLOCK_BYTES = (X3 ? 2 : 1) * SUB_BYTES;   // (X3: hi block, then lo block)
+    static constexpr int BIAS_BLOCK_BYTES = SUB_BYTES;
     static constexpr int STAGE_BYTES = STAGE_BLOCKS * BLOCK_BYTES;
     static constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
-    static constexpr int IN_STAGES = X3 ? 3 : 2;           // conv_input: 9 taps x (K=16: 3 real channels); 16 tap slots (X3: 9)
+    static constexpr int IN_STAGES = (9 + STAGE_BLOCKS - 1) / STAGE_BLOCKS;   // conv_input: 9 taps x (K=16: 3 real channels) in IN_STAGES * STAGE_BLOCKS tap slots
     static constexpr int GROUP_STAGES = (IN_STAGES + 1) + NET_LAYERS * (STAGES_PER_LAYER + 1);   // every layer starts with its bias block
     // LT = 2 has TMEM for two accumulators per tile (4 x 128 = 512 columns): the layers alternate between them, and the
     // epilogue publishes its output per 16-column chunk (NQ act_ready barriers per tile), so the MMAs of layer L+1
@@ -91,7 +101,8 @@ __host__ __device__ inline int group_positions(int n_pos, int n_pairs) {
 
 // the kernel body (a __device__ function so that net_auto.cu can put it behind a device-side dispatch together with
 // pp::trunk_pp_body); the __global__ wrappers are in net_tc2.cu
-template <int LT, bool X3 = false>
+// (PAIR: the three weight arrays hold per-CTA halves, stage-major: [stage][2 ranks][STAGE_BLOCKS blocks]([hi, lo])[2][64][8])
+template <int LT, bool X3 = false, bool PAIR = false>
 __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__ wq,   // [32][72 K-blocks][2][128][8] bf16 (X3: [32][72][hi, lo][2][128][8])
                  const __nv_bfloat16* __restrict__ wq_in,// conv_input: [16 tap slots (9 used)][2][128][8] bf16 (X3: [9 taps][hi, lo][2][128][8])
                  const __nv_bfloat16* __restrict__ wq_bias,   // [33][2][128][8] bf16: per layer the BN shift as a K=16 B block
@@ -106,7 +117,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                  const int* src_rows = nullptr,          // slot mode: position i of this CTA pair reads planes row src_rows[i]
                  int pos_base = 0, bool solo = false) {  // solo: this CTA pair alone evaluates the n_pos_known positions that
                                                          // start at row pos_base of planes / headfeat (trunk_x3_kernel)
-    using C = Cfg<LT, X3>;
+    using C = Cfg<LT, X3, PAIR>;
     constexpr int LOC_TILES = C::LOC_TILES, MAX_P = C::MAX_P, PANEL_BYTES = C::PANEL_BYTES, A_BYTES = C::A_BYTES,
                   STAGES = C::STAGES, BAR_OFF = C::BAR_OFF, EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS,
                   SKIP_ROWS = C::SKIP_ROWS, NQ = C::NQ, STAGE_BLOCKS = C::STAGE_BLOCKS, STAGE_BYTES = C::STAGE_BYTES,
@@ -129,7 +140,8 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
     const int tile0 = (rank == 0) ? 0 : T0;           // first global tile of this CTA
     const int n_groups = (n_pos + P - 1) / P;
     if (pair >= n_groups) return;                     // both CTAs of the pair take the same branch
-    const bool has_peer = (T - T0) > 0;
+    const int T1 = T - T0;                            // tiles of rank 1 (<= T0)
+    const bool has_peer = T1 > 0;
 
     uint8_t* sA = smem;
     const uint32_t sA_u = smem_u32(sA);
@@ -145,21 +157,34 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
     const int bnd_quarter = (rank == 0) ? 3 : 0;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; i++) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, tiles > 0 ? tiles : 1); }
+        for (int i = 0; i < STAGES; i++) {
+            // PAIR: the leader's full barrier also counts the peer's forwarded "my half has landed"; a stage is released in
+            // both CTAs by the multicast commits of the leader's T0 issuers
+            mbar_init(bar_full + 8 * i, (PAIR && rank == 0) ? 2 : 1);
+            mbar_init(bar_empty + 8 * i, PAIR ? T0 : (tiles > 0 ? tiles : 1));
+        }
         for (int t = 0; t < LOC_TILES; t++) {
             mbar_init(bar_accum + 8 * t, 1);
             int c = 8 + (t > 0 ? 2 : 0) + (t < tiles - 1 ? 2 : 0);      // (the peer's halo rows arrive as transaction bytes)
+            if (PAIR && rank == 0 && t < T1) c += 1;                    // the peer's forwarded "my rows of tile pair t are in place"
             for (int q = 0; q < NQ; q++) mbar_init(bar_act + 8 * (t * NQ + q), c);
         }
         mbar_init(bar_bnd, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == EPI_WARPS + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
-                     "r"(C::TMEM_COLS)
-                     : "memory");
-        // (solo: the body runs again in this launch and allocates again -- a CTA that gave up its permit may not)
-        if (!solo) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                         "r"(C::TMEM_COLS)
+                         : "memory");
+            if (!solo) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)),
+                         "r"(C::TMEM_COLS)
+                         : "memory");
+            // (solo: the body runs again in this launch and allocates again -- a CTA that gave up its permit may not)
+            if (!solo) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     for (int i = threadIdx.x; i < A_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(sA)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
@@ -267,8 +292,15 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                 mbar_wait_spin<false>(bar_accum + 8 * lt, lpar);
                 if (nb_lo) mbar_wait_spin<false>(bar_accum + 8 * (lt - 1), lpar);
                 if (nb_hi) mbar_wait_spin<false>(bar_accum + 8 * (lt + 1), lpar);
-                if (bnd) mbar_wait_spin<false>(bar_bnd, lpar);    // the peer's boundary-tile MMAs have retired
+                // the peer's boundary-tile MMAs have retired (PAIR: they are the other half of the pair MMAs of index 0 -- rank
+                // 1's first tile -- or T0 - 1 -- rank 0's last tile --, whose multicast commits arrive on this CTA's barrier)
+                if (bnd) {
+                    if constexpr (PAIR) mbar_wait_spin<false>(bar_accum + 8 * ((rank == 0) ? 0 : T0 - 1), lpar);
+                    else mbar_wait_spin<false>(bar_bnd, lpar);
+                }
                 if (dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer >= 0) dbg[layer * 4 + 2] = clock64();
+                const bool detail = dbg && blockIdx.x == 0 && iter == 0 && threadIdx.x == 0 && layer == 20;   // diagnostics: dbg[160..175]
+                if (detail) dbg[160] = clock64();
                 tc_fence_after();
                 float va[16], vb[16];
                 float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f;               // last layer: the heads' 1x1 convolutions of this row
@@ -277,6 +309,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                 for (int ch = 0; ch < 4; ch++) {
                     float* v = (ch & 1) ? vb : va;
                     tmem_ld_wait();
+                    if (detail && ch == 0) dbg[161] = clock64();
                     if (ch < 3) tmem_ld16(tsrc + (uint32_t)((ch + 1) * 16), (ch & 1) ? va : vb);
                     if constexpr (X3) {
 #pragma unroll
@@ -331,9 +364,11 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                             }
                         }
                         if (NQ == 4 || ch == 3) {        // channels 16(4*chalf + ch) .. +15 of these rows are in place
+                            if (detail && ch == 0) dbg[162] = clock64();
                             fence_async_smem();
                             tc_fence_before();
                             __syncwarp();
+                            if (detail && ch == 0) dbg[163] = clock64();
                             if (lane == 0) {
                                 if (NQ == 4) {
                                     publish(ch, (X3 ? 8 : 4) * HALO_BYTES);
@@ -341,6 +376,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                                         push_halo(2 * ch, ch); push_halo(2 * ch + 1, ch);
                                         if (X3) { push_halo(16 + 2 * ch, ch); push_halo(16 + 2 * ch + 1, ch); }
                                     }
+                                    if (detail) dbg[164 + ch] = clock64();
                                 } else {
                                     publish(0, 16 * HALO_BYTES);
                                     if (bnd) {
@@ -371,7 +407,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
             tc_fence_before();
         } else if (warp == EPI_WARPS) {
             // ================= weight producer =================
-            if (tiles == 0) continue;
+            if (PAIR ? (T0 == 0) : (tiles == 0)) continue;      // (PAIR: the peer's half of the B operand is needed whatever it owns)
 #pragma unroll 1
             int gn = iter * GROUP_STAGES;
 #pragma unroll 1
@@ -385,9 +421,11 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                     if (lane == 0) {
                         const __nv_bfloat16* src;
                         uint32_t bytes = STAGE_BYTES;
-                        if (st == 0) { src = wq_bias + (size_t)(layer + 1) * (BIAS_BYTES / 2); bytes = BIAS_BYTES; }   // (sizes in bf16 elements)
-                        else if (layer < 0) src = wq_in + (size_t)(st - 1) * (STAGE_BYTES / 2);
-                        else src = wq + (size_t)(layer * STAGES_PER_LAYER + st - 1) * (STAGE_BYTES / 2);
+                        constexpr int RK = PAIR ? 2 : 1;           // per-CTA halves are stored stage-major: [stage][rank]
+                        const int rk = PAIR ? (int)rank : 0;
+                        if (st == 0) { src = wq_bias + (size_t)((layer + 1) * RK + rk) * (C::BIAS_BLOCK_BYTES / 2); bytes = C::BIAS_BLOCK_BYTES; }   // (sizes in bf16 elements)
+                        else if (layer < 0) src = wq_in + (size_t)((st - 1) * RK + rk) * (STAGE_BYTES / 2);
+                        else src = wq + (size_t)((layer * STAGES_PER_LAYER + st - 1) * RK + rk) * (STAGE_BYTES / 2);
                         mbar_expect_tx(bar_full + 8 * stage, bytes);
                         bulk_g2s(sB_u + stage * STAGE_BYTES, src, bytes, bar_full + 8 * stage);
                     }
@@ -400,15 +438,57 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
             // MMA before it becomes the bottleneck.  Its loop is therefore unrolled over the 18 weight stages of a layer
             // (all K-block offsets are immediates), keeps stage / parity as running counters and waits without back-off.
             const int lt = warp - (EPI_WARPS + 1);
+            if constexpr (PAIR) {
+                if (rank != 0) {
+                    // rank 1 has no MMAs to issue (the leader issues for the pair): its two issuer warps forward its barriers
+                    // to the leader with CTA-scope remote arrives (see net_pp_kernel.cuh).  Warp 0: "my half of weight stage i
+                    // has landed"; warp 1: "chunk q of my rows of tile pair t is in place".  Neither can be lapped: the
+                    // events they wait for need the leader's next MMAs, which need their arrive.
+                    if (lt == 0) {
+                        int gn = iter * GROUP_STAGES;
+#pragma unroll 1
+                        for (int i = 0; i < GROUP_STAGES; i++, gn++) {
+                            const int stage = gn % STAGES;
+                            mbar_wait_spin<false>(bar_full + 8 * stage, (uint32_t)((gn / STAGES) & 1));
+                            if (lane == 0) mbar_arrive_peer(map_to_rank(bar_full + 8 * stage, 0));
+                            __syncwarp();
+                        }
+                    } else if (lt == 1) {
+#pragma unroll 1
+                        for (int layer = -1; layer < NET_LAYERS; layer++) {
+                            const uint32_t apar = (uint32_t)((iter * GROUP_LAYERS + layer + 1) & 1);
+#pragma unroll 1
+                            for (int q = 0; q < NQ; q++)
+#pragma unroll 1
+                                for (int t = 0; t < T1; t++) {
+                                    mbar_wait_spin<false>(bar_act + 8 * (t * NQ + q), apar);
+                                    if (lane == 0) mbar_arrive_peer(map_to_rank(bar_act + 8 * (t * NQ + q), 0));
+                                    __syncwarp();
+                                }
+                        }
+                    }
+                    continue;
+                }
+            }
             if (lt >= tiles) continue;
             const bool leader = elect_one();
             const uint32_t a_tile = sA_u + (uint32_t)(LEAD + lt * 128) * 16u;
-            const bool signal_peer = has_peer && (lt == bnd_tile);
+            const bool signal_peer = !PAIR && has_peer && (lt == bnd_tile);
+            constexpr uint32_t idesc = PAIR ? tcx::IDESC_M256_N128_BF16 : IDESC;
             const uint64_t a_desc = make_desc(a_tile, PANEL_BYTES, 128);         // + (row shift + panel offset) / 16: shared
-            const uint64_t b_desc = make_desc(sB_u, 2048, 128);                  //   addresses are < 256 KiB, no carry
+            const uint64_t b_desc = make_desc(sB_u, C::NCO * 16, 128);           //   addresses are < 256 KiB, no carry
             const uint64_t bias_a = a_desc + (uint64_t)((uint32_t)ACT_PANELS * PANEL_BYTES / 16u);
             constexpr uint64_t A_LO = (uint64_t)(16u * PANEL_BYTES / 16u);      // X3: descriptor offset of the lo panels
-            constexpr uint64_t B_BLK = (uint64_t)(BLOCK_BYTES / 16), B_LO = 256u; // per K-block / X3: of its lo half
+            constexpr uint64_t B_BLK = (uint64_t)(BLOCK_BYTES / 16), B_LO = (uint64_t)(C::SUB_BYTES / 16); // per K-block / X3: of its lo half
+            // one MMA of this tile (PAIR: of this tile and the peer's tile of the same index)
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+                if constexpr (PAIR) umma_bf16_2sm(d, a, b, idesc, acc);
+                else umma_bf16(d, a, b, idesc, acc);
+            };
+            auto commit_accum = [&]() {            // the layer's accumulator is complete when the MMAs issued so far retire
+                if constexpr (PAIR) umma_commit_2sm(bar_accum + 8 * lt, (uint16_t)3);
+                else umma_commit(bar_accum + 8 * lt);
+            };
             int gn = iter * GROUP_STAGES;
             int stage = gn % STAGES;
             uint32_t par = (uint32_t)((gn / STAGES) & 1);
@@ -424,7 +504,8 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                 b_st = b_desc + (uint64_t)(uint32_t)(stage * (STAGE_BYTES / 16));
             };
             auto release_stage = [&]() {           // leader only: frees the stage when the MMAs issued so far retire
-                umma_commit(bar_empty + 8 * stage);
+                if constexpr (PAIR) umma_commit_2sm(bar_empty + 8 * stage, (uint16_t)3);       // (in both CTAs)
+                else umma_commit(bar_empty + 8 * stage);
             };
             auto advance = [&]() {
                 if (++stage == STAGES) { stage = 0; par ^= 1u; }
@@ -442,7 +523,7 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                 }
                 next_stage();
                 if (leader) {
-                    umma_bf16(tmem_d, bias_a, b_st, IDESC, 0u);
+                    mma(tmem_d, bias_a, b_st, 0u);
                     release_stage();
                 }
                 advance();
@@ -457,14 +538,14 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                                 const int tap = STAGE_BLOCKS * s + j;
                                 if (tap < 9) {
                                     const uint64_t a_tap = a_desc + (uint64_t)(int64_t)((tap / 3 - 1) * 10 + (tap % 3 - 1));
-                                    umma_bf16(tmem_d, a_tap, b_st + (uint64_t)j * B_BLK, IDESC, 1u);
+                                    mma(tmem_d, a_tap, b_st + (uint64_t)j * B_BLK, 1u);
                                     // (the input planes are exact in bf16: no lo part on the A side)
-                                    if (X3) umma_bf16(tmem_d, a_tap, b_st + (uint64_t)j * B_BLK + B_LO, IDESC, 1u);
+                                    if (X3) mma(tmem_d, a_tap, b_st + (uint64_t)j * B_BLK + B_LO, 1u);
                                 }
                             }
                             release_stage();
                             if (s == IN_STAGES - 1) {
-                                umma_commit(bar_accum + 8 * lt);
+                                commit_accum();
                                 if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
                             }
                         }
@@ -482,23 +563,25 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
                             if (r == 0 && C::two_accumulators(lt)) {
                                 wait_act(q, apar);
                                 if (q == 0 && dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader) dbg[layer * 4 + 0] = clock64();
+                                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && leader && layer == 21) dbg[168 + q] = clock64();
                             }
                             const int off = (tap / 3 - 1) * 10 + (tap % 3 - 1) + 2 * unit * (PANEL_BYTES / 16);
                             if (leader) {
                                 const uint64_t a_k = a_desc + (uint64_t)(int64_t)off, b_k = b_st + (uint64_t)ks * B_BLK;
-                                umma_bf16(tmem_d, a_k, b_k, IDESC, 1u);
+                                mma(tmem_d, a_k, b_k, 1u);
                                 if (X3) {
-                                    umma_bf16(tmem_d, a_k + A_LO, b_k, IDESC, 1u);
-                                    umma_bf16(tmem_d, a_k, b_k + B_LO, IDESC, 1u);
+                                    mma(tmem_d, a_k + A_LO, b_k, 1u);
+                                    mma(tmem_d, a_k, b_k + B_LO, 1u);
                                 }
                             }
                         }
                         if (leader) {
                             release_stage();
                             if (s == STAGES_PER_LAYER - 1) {
-                                umma_commit(bar_accum + 8 * lt);
+                                commit_accum();
                                 if (signal_peer) umma_commit_mcast(bar_bnd, (uint16_t)(1u << peer));
                                 if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0) dbg[layer * 4 + 1] = clock64();
+                                if (dbg && blockIdx.x == 0 && iter == 0 && lt == 0 && layer == 20) dbg[172] = clock64();
                             }
                         }
                         advance();
@@ -514,7 +597,8 @@ __device__ __forceinline__ void trunk_tc2_body(const __nv_bfloat16* __restrict__
     __syncthreads();
     cluster_sync_all();                 // nobody exits while the peer may still write its margins / barriers
     if (warp == EPI_WARPS + 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
     }
     if (solo && threadIdx.x == 0) {     // the body runs again in this launch: leave no valid mbarrier objects behind
         for (uint32_t b = bar_u; b < bar_bnd + 8; b += 8) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(b) : "memory");
