@@ -458,9 +458,9 @@ def main():
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         # dominant kernel = the residual trunk (tcgen05 implicit GEMM); rank 0's launches
         achieved_tf = (evals * TRUNK_FLOP_PER_POSITION / (trunk_ms / 1e3)) / 1e12 if trunk_ms > 0 else 0.0
-        kernel = {"bf16": "trunk_auto_kernel (one launch per round; on the device: trunk_tc2_body<2> up to 370 positions, "
-                          "trunk_pp_body<1> with cta_group::2 MMAs above)",
-                  "bf16x3": "trunk_x3_kernel (trunk_tc2_body<2, X3>: 3 MMAs per K-block, hi*hi + lo*hi + hi*lo)",
+        kernel = {"bf16": "trunk_auto_kernel (one launch per round; on the device: trunk_tc2_body<2> up to 370 positions -- with "
+                          "cta_group::2 MMAs up to 148 --, trunk_pp_body<1> with cta_group::2 MMAs above)",
+                  "bf16x3": "trunk_x3_kernel (trunk_tc2_body<2, X3, PAIR>: 3 cta_group::2 MMAs per K-block, hi*hi + lo*hi + hi*lo)",
                   "fp32": "conv3x3_fp32_kernel"}[args.numerics]
         out = {
             "metric": "self-play moves/sec (50 sims/move)", "value": value, "unit": "moves/s",
