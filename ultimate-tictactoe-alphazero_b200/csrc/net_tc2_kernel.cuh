@@ -30,7 +30,6 @@ namespace tc2 {
 
 constexpr int POS_ROWS = 100;
 constexpr int LEAD = 11;
-constexpr int BIAS_BYTES = 4096;                // one [2 panels][128 co][8] block: BN shift as bf16 hi + lo (+ lo2) in k = 0, 1 (, 2)
 constexpr int GROUP_LAYERS = NET_LAYERS + 1;     // conv_input runs as layer -1 through the same pipeline
 constexpr uint32_t IDESC = tcx::IDESC_M128_N128_BF16;
 
@@ -64,7 +63,7 @@ struct Cfg {
     static constexpr int NCO = PAIR ? 64 : 128;            // output channels of the B operand held by this CTA
     static constexpr int SUB_BYTES = 2 * NCO * 16;         // one [2 k-panels][NCO co][8] bf16 block
     static constexpr int BLOCK_BYTES = (X3 ? 2 : 1) * SUB_BYTES;   // (X3: hi block, then lo block)
-    static constexpr int BIAS_BLOCK_BYTES = SUB_BYTES;
+    static constexpr int BIAS_BLOCK_BYTES = SUB_BYTES;     // the BN shift as one block: bf16 hi + lo (+ lo2) in k = 0, 1 (, 2)
     static constexpr int STAGE_BYTES = STAGE_BLOCKS * BLOCK_BYTES;
     static constexpr int STAGES_PER_LAYER = 72 / STAGE_BLOCKS;
     static constexpr int IN_STAGES = (9 + STAGE_BLOCKS - 1) / STAGE_BLOCKS;   // conv_input: 9 taps x (K=16: 3 real channels) in IN_STAGES * STAGE_BLOCKS tap slots
