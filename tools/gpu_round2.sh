@@ -19,4 +19,10 @@ ncu --set full --clock-control none --import-source on -k regex:trunk_auto -s 20
 ncu --set full --clock-control none --import-source on -k regex:trunk_auto -s 3 -c 1 -f -o gpurun_out/prof_trunk2_r2 python tools/trunk_timeline.py 345 > gpurun_out/ncu2_r2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:trunk_x3 -s 3 -c 1 -f -o gpurun_out/prof_trunkx3_r2 python tools/fwd_loop.py 500 6 bf16x3 > gpurun_out/ncu_x3_r2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tree_round -s 200 -c 1 -f -o gpurun_out/prof_tree_r2 python tools/prof_selfplay.py --games 500 > gpurun_out/ncu4_r2.log 2>&1
+# rules kernels (plain runs: 2^22 and 2^24 positions) and the micro-benchmarks behind DESIGN.md section 9
+python tools/prof_rules.py 22 > gpurun_out/rules_plain22.log 2>&1; cp gpurun_out/rules_points.json gpurun_out/rules_points22.json
+python tools/prof_rules.py 24 > gpurun_out/rules_plain24.log 2>&1; cp gpurun_out/rules_points.json gpurun_out/rules_points24.json
+mkdir -p build
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o build/mma_shapes tools/micro/mma_shapes.cu && build/mma_shapes > gpurun_out/mma_shapes.txt 2>&1
+nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/nt_skeleton tools/micro/nt_skeleton.cu && build/nt_skeleton > gpurun_out/nt_skeleton.txt 2>&1
 tail -3 gpurun_out/t_gpu_r2.log
