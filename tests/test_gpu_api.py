@@ -196,3 +196,46 @@ def test_dirichlet_root_noise_distribution(alpha, L):
     y = engine.dirichlet_samples(17, 0, 64, L, alpha).cpu().numpy()
     z = engine.dirichlet_samples(18, 0, 64, L, alpha).cpu().numpy()
     assert (y == x[:64].astype(np.float32)).all() and (y != z).any()
+
+
+def test_reference_test_script_flow_with_a_python_inference_closure():
+    """The reference's own smoke test of its native module (test_cpp_mcts.py:22-101), step by step through the drop-in
+    modules: State(), legal_actions(), to_input_tensor(), then uttt_cpp.pv_mcts_scores(model=<Python closure over a
+    DualNetwork>, state, temperature=1.0, evaluate_count=10, batch_size=2).  Beyond the script's own checks (243 floats,
+    one score per legal action, scores sum to 1) the closure's outputs are recorded and the reference search fed exactly
+    those rows (cpp/python_bindings.cpp:11-47 contract) must return the same float scores bit for bit."""
+    import torch
+    import uttt_cpp
+    from dual_network import DualNetwork
+    torch.manual_seed(0)
+    model = DualNetwork().eval()
+    state = uttt_cpp.State()
+    legal = state.legal_actions()
+    assert len(legal) == 81 and legal[:5] == [0, 1, 2, 3, 4]                     # test_cpp_mcts.py:24-29
+    tensor = state.to_input_tensor()
+    assert len(tensor) == 243 and np.array(tensor, np.float32).reshape(9, 9, 3)[..., 2].sum() == 81     # :32-36
+    seen_states, seen_pol, seen_val, calls = [], [], [], []
+
+    def inference(states_list):                                                  # test_cpp_mcts.py:40-66
+        calls.append(len(states_list))
+        x = np.stack([np.array(s.to_input_tensor(), np.float32).reshape(9, 9, 3) for s in states_list]).transpose(0, 3, 1, 2)
+        with torch.no_grad():
+            policies, values = model(torch.from_numpy(np.ascontiguousarray(x)))
+        out = []
+        for i, s in enumerate(states_list):
+            pol, val = policies[i].numpy().copy(), float(values[i][0])
+            seen_states.append(s.packed().copy()); seen_pol.append(pol); seen_val.append(np.float32(val))
+            out.append((pol, val))
+        return out
+    one = inference([state])                                                     # :69-73
+    assert abs(float(one[0][0].sum()) - 1.0) < 1e-5 and -1.0 <= one[0][1] <= 1.0
+    seen_states.clear(); seen_pol.clear(); seen_val.clear(); calls.clear()
+    scores = uttt_cpp.pv_mcts_scores(model=inference, state=state, temperature=1.0, evaluate_count=10, batch_size=2)   # :78-83
+    assert isinstance(scores, list) and len(scores) == len(legal)                # :96-99
+    assert abs(sum(scores) - 1.0) < 1e-6 and calls == [2, 2, 2, 2, 2]
+    # the reference queues the same leaf k times (Q-M3): one row per distinct evaluation is what the table replay consumes
+    keep = np.cumsum([0] + calls[:-1])
+    want, miss, unused = O.table_mcts(state.packed(), 1.0, 10, 2, np.array(seen_states)[keep], np.array(seen_pol)[keep],
+                                      np.array(seen_val)[keep])
+    assert miss == 0 and unused == 0
+    assert np.array(scores, np.float32).tobytes() == want.tobytes()
