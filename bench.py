@@ -160,7 +160,10 @@ def timed_selfplay(c, eng, ev_kind, steps, warmup, games, seed0):
                                    game0=(seed0 + i * c.world + c.rank) * games, stream=c.stream)
     for i in range(warmup):
         step(1000 + i)
-    out = {"dev_ms": 0.0, "plies": 0, "sims": 0, "evals": 0, "rounds": 0, "trunk_ms": 0.0, "trunk_launches": 0, "launches": 0}
+    # trunk_*: the trunk launches that were bracketed by CUDA events (the engine brackets every 4th window of 8 rounds: an event
+    # between two kernels defeats their programmatic dependent launch, bracketing every launch costs 1.6 % of the step)
+    out = {"dev_ms": 0.0, "plies": 0, "sims": 0, "evals": 0, "rounds": 0, "trunk_ms": 0.0, "trunk_launches": 0, "trunk_evals": 0,
+           "launches": 0}
     c.barrier()
     for i in range(steps):
         c.flush.fill_(i & 0xFF)                    # evict L2 between timed steps (not timed)
@@ -172,7 +175,8 @@ def timed_selfplay(c, eng, ev_kind, steps, warmup, games, seed0):
         out["dev_ms"] += e0.elapsed_time(e1)
         out["plies"] += int(st[0]); out["sims"] += int(st[1]); out["evals"] += int(st[2]); out["rounds"] += int(st[3])
         prof = eng.last_run_profile()
-        out["trunk_ms"] += prof["trunk"][0]; out["trunk_launches"] += prof["trunk"][1]; out["launches"] += prof["all"][1]
+        tt = prof["trunk_timed"]
+        out["trunk_ms"] += tt[0]; out["trunk_launches"] += tt[1]; out["trunk_evals"] += tt[2]; out["launches"] += prof["all"][1]
     c.barrier()
     return out
 
@@ -389,7 +393,7 @@ def main():
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.stop() if rank == 0 else None
     dev_ms, plies, evals, rounds = leg["dev_ms"], leg["plies"], leg["evals"], leg["rounds"]
-    trunk_ms, trunk_launches = leg["trunk_ms"], leg["trunk_launches"]
+    trunk_ms, trunk_launches, trunk_evals = leg["trunk_ms"], leg["trunk_launches"], leg["trunk_evals"]
     # diagnostic, outside the timed region: one more cycle with every kernel bracketed by events (level 2 costs ~1.5 %
     # of a cycle in GPU idle time at the extra event boundaries, which is why the timed steps only bracket the trunk)
     eng.set_profile_level(2)
@@ -457,7 +461,8 @@ def main():
         value = plies_all / (dev_ms_max / 1e3)
         peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
         # dominant kernel = the residual trunk (tcgen05 implicit GEMM); rank 0's launches
-        achieved_tf = (evals * TRUNK_FLOP_PER_POSITION / (trunk_ms / 1e3)) / 1e12 if trunk_ms > 0 else 0.0
+        achieved_tf = (trunk_evals * TRUNK_FLOP_PER_POSITION / (trunk_ms / 1e3)) / 1e12 if trunk_ms > 0 else 0.0
+        trunk_est_ms = trunk_ms / max(trunk_launches, 1) * rounds          # all launches of the timed region at the sampled average
         kernel = {"bf16": "trunk_auto_kernel (one launch per round; on the device: trunk_tc2_body<2> up to 370 positions -- with "
                           "cta_group::2 MMAs up to 148 --, trunk_pp_body<1> with cta_group::2 MMAs above)",
                   "bf16x3": "trunk_x3_kernel (trunk_tc2_body<2, X3, PAIR>: 3 cta_group::2 MMAs per K-block, hi*hi + lo*hi + hi*lo)",
@@ -484,11 +489,17 @@ def main():
                          "traffic_unit": "bytes per launch from a cold-cache ncu capture (bf16: 1.56x the 9.9 MB algorithmic -- the weights "
                                          "come from DRAM once per capture, from L2 in steady state); tensor-bound kernel: informational",
                          "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
-                         "flop_per_launch": evals * TRUNK_FLOP_PER_POSITION / max(trunk_launches, 1),
+                         "flop_per_launch": trunk_evals * TRUNK_FLOP_PER_POSITION / max(trunk_launches, 1),
                          "flop_convention": "useful (algorithmic) FLOPs: 764.4 MFLOP per evaluated position, SURVEY 8(d)"
                                             + ("; the kernel issues 3x that on the tensor pipe" if args.numerics == "bf16x3" else ""),
-                         "avg_launch_ms": trunk_ms / max(trunk_launches, 1), "launches": trunk_launches},
-            "breakdown_ms_rank0": {"trunk": trunk_ms, "tree_heads_and_gaps": dev_ms - trunk_ms, "device_total": dev_ms,
+                         "avg_launch_ms": trunk_ms / max(trunk_launches, 1), "launches": trunk_launches,
+                         "timed_with": "CUDA events on the launching stream around %d of the %d trunk launches of the timed region (every "
+                                       "launch of every 4th window of 8 rounds: a uniform sample of the cycle's batch sizes), which "
+                                       "evaluated %d of its %d positions; an event between two kernels defeats their programmatic "
+                                       "dependent launch, and bracketing every launch costs 1.6 %% of the step (UTTT_PROFILE_SAMPLE=1)"
+                                       % (trunk_launches, rounds, trunk_evals, evals)},
+            "breakdown_ms_rank0": {"trunk_timed_launches": trunk_ms, "trunk_all_launches_at_that_average": trunk_est_ms,
+                                   "tree_heads_and_gaps": dev_ms - trunk_est_ms, "device_total": dev_ms,
                                    "rounds": rounds, "evals": evals, "plies": plies,
                                    "one_extra_cycle_with_all_kernels_timed": split},
             "wall_s": wall_s,
@@ -496,7 +507,7 @@ def main():
         }
         if x3 is not None:
             l3 = x3["leg"]
-            a3 = (l3["evals"] * TRUNK_FLOP_PER_POSITION / (l3["trunk_ms"] / 1e3)) / 1e12 if l3["trunk_ms"] > 0 else 0.0
+            a3 = (l3["trunk_evals"] * TRUNK_FLOP_PER_POSITION / (l3["trunk_ms"] / 1e3)) / 1e12 if l3["trunk_ms"] > 0 else 0.0
             out["bf16x3"] = {
                 "what": "the same workload and the same two measurements with UTTT_EVAL_NET_BF16X3 (split-bf16 operands: policy / "
                         "value within 1e-2 of the fp32 reference forward on these random-init weights, tests/test_gpu_net.py)",

@@ -227,12 +227,16 @@ int uttt_samples_unpack(const void *samples_dev, int64_t n, float *x_dev, float 
                         void *stream);
 
 /* timing of the engine's own kernels during the last uttt_selfplay_run*: CUDA-event ms on the
- * launching stream and launch counts; kind: 0 tree kernels, 1 trunk, 2 heads, 3 everything */
+ * launching stream and launch counts; kind: 0 tree kernels, 1 trunk, 2 heads, 3 everything (ms: of the launches that were
+ * bracketed by events, see uttt_set_profile_level; counts: of all launches); 4: the bracketed trunk launches (their ms,
+ * their number), 5: the same ms and the number of positions those launches evaluated */
 int uttt_last_run_profile(uttt_engine *e, int kind, double *ms_out, int64_t *launches_out);
 
 /* which of those kernels are bracketed by CUDA events during self-play (an event between two dependent kernels costs
- * about 1 us of GPU idle time): 0 none, 1 the trunk only (default: what the roofline needs), 2 tree / trunk / heads
- * (kind 0, 2, 3 of uttt_last_run_profile report 0 ms below level 2).  Launch counts are always kept. */
+ * about 1 us of GPU idle time and defeats their programmatic dependent launch): 0 none, 1 the trunk only, and only in
+ * every 4th window of 8 rounds (default: what the roofline needs -- a uniform sample of the launches; UTTT_PROFILE_SAMPLE=1
+ * brackets every launch), 2 tree / trunk / heads in every round (kind 0, 2, 3 of uttt_last_run_profile report 0 ms below
+ * level 2).  Launch counts are always kept. */
 int uttt_set_profile_level(uttt_engine *e, int level);
 
 /* diagnostics: clock64 timeline of CTA 0 of the last tensor-core trunk launch, [32 layers][4]:

@@ -408,6 +408,12 @@ def test_profile_levels_and_identical_play(setup):
             prof = e.last_run_profile()
             assert (prof["tree"][0] > 0) == tree_timed and (prof["trunk"][0] > 0) == trunk_timed, (level, prof)
             assert prof["trunk"][1] == st[3] and prof["all"][1] >= 2 * st[3]            # one trunk launch per round
+            # the launches that were bracketed: none / every 4th window of 8 rounds / all, with the positions they evaluated
+            t_ms, t_n, t_ev = prof["trunk_timed"]
+            assert t_ms == prof["trunk"][0] and 0 <= t_ev <= st[2]
+            assert t_n == (0 if level == 0 else (st[3] if level == 2 else 8 * ((st[3] // 8 + 3) // 4)))
+            if level == 2:
+                assert t_ev == st[2]
             h = e.selfplay_fetch(12)
             hists.append((h.lens.copy(), h.actions.copy(), h.counts.copy()))
         for other in hists[1:]:

@@ -30,11 +30,11 @@ for r in range(a.reps):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     prof = e.last_run_profile()
-    flop = int(st[2]) * 32 * 2 * 81 * 128 * 1152
-    print("games=%d plies=%d evals=%d rounds=%d wall=%.3fs moves/s=%.0f | tree %.1f ms trunk %.1f ms (%.1f TFLOP/s, %.3f ms/launch) heads %.1f ms"
-          % (a.games, st[0], st[2], st[3], dt, st[0] / dt, prof["tree"][0], prof["trunk"][0],
-             flop / (prof["trunk"][0] / 1e3) / 1e12 if prof["trunk"][0] else 0, prof["trunk"][0] / max(prof["trunk"][1], 1),
-             prof["heads"][0]))
+    t_ms, t_n, t_ev = prof["trunk_timed"]          # the trunk launches bracketed by events (all of them at profile level 2)
+    flop = t_ev * 32 * 2 * 81 * 128 * 1152
+    print("games=%d plies=%d evals=%d rounds=%d wall=%.3fs moves/s=%.0f | tree %.1f ms trunk %.1f ms (%.1f TFLOP/s, %.3f ms/launch, %d launches timed) heads %.1f ms"
+          % (a.games, st[0], st[2], st[3], dt, st[0] / dt, prof["tree"][0], t_ms,
+             flop / (t_ms / 1e3) / 1e12 if t_ms else 0, t_ms / max(t_n, 1), t_n, prof["heads"][0]))
     h = e.batch_histogram()
     print("  evaluator batch sizes (positions: launches): " +
           " ".join("%d-%d:%d" % (16 * i, 16 * i + 15, n) for i, n in enumerate(h) if n))

@@ -92,6 +92,8 @@ struct uttt_engine {
     uint8_t* slot_flags;    // [n_slots] slot mode of the evaluator queue (see net_auto.cu)
     long long* tc_dbg;      // [32][4] clock64 timeline of trunk CTA 0, then [64] histogram of batch sizes (diagnostics)
     int prof_level;         // self-play kernel timing: 2 = tree / trunk / heads events every round, 1 = trunk only, 0 = none
+    int prof_sample;        // level 1: the trunk is bracketed in every prof_sample-th window of rounds only (see uttt_set_profile_level)
+    int64_t prof_sampled_launches, prof_sampled_evals;      // trunk launches with events in the last run, positions they evaluated
     int lane_threshold;     // slots from which self-play splits into two overlapped lanes
     int trunk_variant;      // 4 (default): CTA pair per group (net_tc2) up to 370 positions, two groups in flight per pair with
                             // cta_group::2 MMAs (net_pp) above, chosen on the device inside ONE launch (net_auto.cu); 3 (kept
@@ -307,6 +309,8 @@ int uttt_create(const uttt_config* cfg, uttt_engine** out) {
     e->progress_user = nullptr;
     e->trunk_variant = getenv("UTTT_TRUNK") ? atoi(getenv("UTTT_TRUNK")) : 4;
     e->prof_level = getenv("UTTT_PROFILE") ? atoi(getenv("UTTT_PROFILE")) : 1;
+    e->prof_sample = getenv("UTTT_PROFILE_SAMPLE") ? atoi(getenv("UTTT_PROFILE_SAMPLE")) : 4;
+    if (e->prof_sample < 1) e->prof_sample = 1;
     e->lane_threshold = getenv("UTTT_LANE_THRESHOLD") ? atoi(getenv("UTTT_LANE_THRESHOLD")) : 1024;
     cudaDeviceProp prop;
     UTTT_CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
@@ -834,6 +838,7 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     UTTT_CUDA_OK(cudaSetDevice(e->cfg.device));
     cudaStream_t s = stream ? (cudaStream_t)stream : e->stream;
     for (int i = 0; i < 4; i++) { e->prof_ms[i] = 0.0; e->prof_launches[i] = 0; }
+    e->prof_sampled_launches = e->prof_sampled_evals = 0;
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (n_games == 0) return 0;
     if (wait_for_forward(e, s)) return 1;
@@ -895,7 +900,16 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     // so the GPU never idles while the host reads the progress counters and the per-kernel event times (one window at
     // a time, that wait cost ~230 us of GPU idle time per window = 4 % of a 500-game cycle).  The price is up to one
     // extra window of rounds after the last game ended (every kernel of such a round exits at once).
+    // Level 1 brackets the trunk launches of every prof_sample-th window only: an event record between two kernels defeats
+    // their programmatic dependent launch, and bracketing every round costs 1.6 % of a 500-game cycle (183 k -> 180 k
+    // moves/s); the positions those launches evaluated come from the evaluation counter in the windows' progress copies.
+    int64_t n_enqueued = 0;
+    bool win_sampled[N_WINDOWS] = {};
+    unsigned long long last_evals = 0;
     auto enqueue_window = [&](int slot) -> int {
+        const bool sampled = e->prof_level >= 2 || (e->prof_level == 1 && n_enqueued % e->prof_sample == 0);
+        win_sampled[slot] = sampled;
+        n_enqueued++;
         for (int i = 0; i < CHECK_EVERY; i++, r++) {
             for (int l = 0; l < n_lanes; l++) {
                 cudaEvent_t* ev = e->ev + 4 * ((slot * CHECK_EVERY + i) * N_LANES + l);
@@ -905,7 +919,7 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
                 e->prof_launches[0] += 1;
                 if (run_evaluator(e, lane_bufs[l], evaluator, lane_tp[l].nn_count + lane_tp[l].parity,
                                   lane_trees[l] * rows_per_tree,
-                                  ls[l], e->prof_level >= 1 ? ev + 1 : nullptr))
+                                  ls[l], sampled ? ev + 1 : nullptr))
                     return 1;
                 if (e->trace_on && !tp && trace_round(e, lane_tp[l], lane_bufs[l], lane_tp[l].nn_count + lane_tp[l].parity, ls[l]))
                     return 1;
@@ -922,7 +936,7 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
             for (int l = 0; l < n_lanes; l++) {
                 float ms = 0.f;
                 cudaEvent_t* ev = e->ev + 4 * ((slot * CHECK_EVERY + i) * N_LANES + l);
-                if (e->prof_level >= 1) { cudaEventElapsedTime(&ms, ev[1], ev[2]); e->prof_ms[1] += ms; }
+                if (win_sampled[slot]) { cudaEventElapsedTime(&ms, ev[1], ev[2]); e->prof_ms[1] += ms; e->prof_sampled_launches += 1; }
                 if (e->prof_level >= 2) {
                     cudaEventElapsedTime(&ms, ev[0], ev[1]); e->prof_ms[0] += ms;
                     cudaEventElapsedTime(&ms, ev[2], ev[3]); e->prof_ms[2] += ms;
@@ -931,6 +945,9 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
             }
         }
         const unsigned long long* hc = e->h_counters + 8 * (1 + slot);
+        // (every leaf queued by a tree round of this window was evaluated by a trunk launch of this window)
+        if (win_sampled[slot]) e->prof_sampled_evals += (int64_t)(hc[4] - last_evals);
+        last_evals = hc[4];
         UTTT_CHECK(hc[5] == 0, "tree node arena overflow (node_cap=%d)", e->node_cap);
         // lane 0's copy may predate lane 1's last rounds: "done" only ever lags, never leads
         done = (int64_t)hc[1] >= n_games;
@@ -1112,9 +1129,14 @@ int uttt_set_profile_level(uttt_engine* e, int level) {
 }
 
 int uttt_last_run_profile(uttt_engine* e, int kind, double* ms_out, int64_t* launches_out) {
-    UTTT_CHECK(e && kind >= 0 && kind < 4, "bad argument");
-    if (ms_out) *ms_out = e->prof_ms[kind];
-    if (launches_out) *launches_out = e->prof_launches[kind];
+    UTTT_CHECK(e && kind >= 0 && kind < 6, "bad argument");
+    if (kind < 4) {
+        if (ms_out) *ms_out = e->prof_ms[kind];
+        if (launches_out) *launches_out = e->prof_launches[kind];
+    } else {            // the trunk launches that were bracketed by events: 4 -> (their ms, their number), 5 -> (their ms, positions)
+        if (ms_out) *ms_out = e->prof_ms[1];
+        if (launches_out) *launches_out = kind == 4 ? e->prof_sampled_launches : e->prof_sampled_evals;
+    }
     return 0;
 }
 

@@ -526,10 +526,16 @@ class Engine:
         _check(self.lib.uttt_set_profile_level(self.h, int(level)))
 
     def last_run_profile(self):
-        """-> {kind: (ms, launches)} for tree / trunk / heads / all kernels of the last self-play run"""
+        """-> {kind: (ms, launches)} for tree / trunk / heads / all kernels of the last self-play run (ms: of the launches
+        bracketed by CUDA events at the engine's profile level, launches: all), plus "trunk_timed": (ms, number, positions) of
+        the trunk launches that were bracketed (profile level 1: every 4th window of rounds)"""
         out = {}
         for kind, name in enumerate(("tree", "trunk", "heads", "all")):
             ms, n = C.c_double(), C.c_int64()
             _check(self.lib.uttt_last_run_profile(self.h, kind, C.byref(ms), C.byref(n)))
             out[name] = (ms.value, n.value)
+        ms, n, ev = C.c_double(), C.c_int64(), C.c_int64()
+        _check(self.lib.uttt_last_run_profile(self.h, 4, C.byref(ms), C.byref(n)))
+        _check(self.lib.uttt_last_run_profile(self.h, 5, None, C.byref(ev)))
+        out["trunk_timed"] = (ms.value, n.value, ev.value)
         return out
