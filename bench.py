@@ -161,7 +161,7 @@ def timed_selfplay(c, eng, ev_kind, steps, warmup, games, seed0):
     for i in range(warmup):
         step(1000 + i)
     # trunk_*: the trunk launches that were bracketed by CUDA events (the engine brackets every 4th window of 8 rounds: an event
-    # between two kernels defeats their programmatic dependent launch, bracketing every launch costs 1.6 % of the step)
+    # record on either side of every trunk launch costs 1.6 % of the step)
     out = {"dev_ms": 0.0, "plies": 0, "sims": 0, "evals": 0, "rounds": 0, "trunk_ms": 0.0, "trunk_launches": 0, "trunk_evals": 0,
            "launches": 0}
     c.barrier()
@@ -495,8 +495,8 @@ def main():
                          "avg_launch_ms": trunk_ms / max(trunk_launches, 1), "launches": trunk_launches,
                          "timed_with": "CUDA events on the launching stream around %d of the %d trunk launches of the timed region (every "
                                        "launch of every 4th window of 8 rounds: a uniform sample of the cycle's batch sizes), which "
-                                       "evaluated %d of its %d positions; an event between two kernels defeats their programmatic "
-                                       "dependent launch, and bracketing every launch costs 1.6 %% of the step (UTTT_PROFILE_SAMPLE=1)"
+                                       "evaluated %d of its %d positions; bracketing every launch costs 1.6 %% of the step and gives the same "
+                                       "average (UTTT_PROFILE_SAMPLE=1)"
                                        % (trunk_launches, rounds, trunk_evals, evals)},
             "breakdown_ms_rank0": {"trunk_timed_launches": trunk_ms, "trunk_all_launches_at_that_average": trunk_est_ms,
                                    "tree_heads_and_gaps": dev_ms - trunk_est_ms, "device_total": dev_ms,

@@ -233,7 +233,7 @@ int uttt_samples_unpack(const void *samples_dev, int64_t n, float *x_dev, float 
 int uttt_last_run_profile(uttt_engine *e, int kind, double *ms_out, int64_t *launches_out);
 
 /* which of those kernels are bracketed by CUDA events during self-play (an event between two dependent kernels costs
- * about 1 us of GPU idle time and defeats their programmatic dependent launch): 0 none, 1 the trunk only, and only in
+ * about 1 us of GPU idle time): 0 none, 1 the trunk only, and only in
  * every 4th window of 8 rounds (default: what the roofline needs -- a uniform sample of the launches; UTTT_PROFILE_SAMPLE=1
  * brackets every launch), 2 tree / trunk / heads in every round (kind 0, 2, 3 of uttt_last_run_profile report 0 ms below
  * level 2).  Launch counts are always kept. */

@@ -900,9 +900,9 @@ int uttt_selfplay_run_device(uttt_engine* e, int64_t n_games, uint64_t game0, in
     // so the GPU never idles while the host reads the progress counters and the per-kernel event times (one window at
     // a time, that wait cost ~230 us of GPU idle time per window = 4 % of a 500-game cycle).  The price is up to one
     // extra window of rounds after the last game ended (every kernel of such a round exits at once).
-    // Level 1 brackets the trunk launches of every prof_sample-th window only: an event record between two kernels defeats
-    // their programmatic dependent launch, and bracketing every round costs 1.6 % of a 500-game cycle (183 k -> 180 k
-    // moves/s); the positions those launches evaluated come from the evaluation counter in the windows' progress copies.
+    // Level 1 brackets the trunk launches of every prof_sample-th window only: the two event records per round cost 1.6 % of a
+    // 500-game cycle (183 k -> 180 k moves/s, with or without programmatic dependent launch); the positions those launches
+    // evaluated come from the evaluation counter in the windows' progress copies.
     int64_t n_enqueued = 0;
     bool win_sampled[N_WINDOWS] = {};
     unsigned long long last_evals = 0;

@@ -211,6 +211,8 @@ __global__ void __launch_bounds__(128) heads_kernel(NetWeights W, const float* _
 __global__ void __launch_bounds__(HEADS_THREADS) heads_fc_kernel(HeadsFC W, const float* __restrict__ headfeat,
                                                                  const int32_t* __restrict__ count, float* __restrict__ policy,
                                                                  float* __restrict__ value, int row_stride) {
+    pdl_trigger();          // (programmatic dependent launch, common.cuh: the next kernel of the round loop may be scheduled)
+    pdl_wait();             // the trunk kernel has finished: its head features are visible
     const int row0 = blockIdx.x * HEADS_P;
     const int n = *count;
     if (row0 >= n) return;
@@ -226,9 +228,8 @@ cudaError_t launch_heads_fc(const NetWeights& w, const float* headfeat, const in
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    heads_fc_kernel<<<(max_rows + HEADS_P - 1) / HEADS_P, HEADS_THREADS, HEADS_SMEM_BYTES, s>>>(heads_fc_of(w), headfeat, count, policy,
-                                                                                                 value, row_stride);
-    return cudaGetLastError();
+    return launch_pdl(heads_fc_kernel, dim3((max_rows + HEADS_P - 1) / HEADS_P), dim3(HEADS_THREADS), HEADS_SMEM_BYTES, s, heads_fc_of(w),
+                      headfeat, count, policy, value, row_stride);
 }
 
 cudaError_t launch_conv_input(const NetWeights& w, const __nv_bfloat16* planes, const int32_t* count, int max_rows,

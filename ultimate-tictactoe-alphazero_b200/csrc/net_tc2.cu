@@ -33,6 +33,8 @@ trunk_x3_kernel(const __nv_bfloat16* __restrict__ wq, const __nv_bfloat16* __res
                 const __nv_bfloat16* __restrict__ wq_bias, const __nv_bfloat16* __restrict__ planes,
                 const float* __restrict__ headw, float* headfeat, uint4* skip, const int32_t* __restrict__ count,
                 long long* dbg) {
+    pdl_trigger();          // the heads kernel behind this one may be scheduled (it waits for this grid's head features)
+    pdl_wait();             // this round's tree kernel has finished: queue length and planes are visible
     const int n_pos = *count;
     if (n_pos <= 0) return;
     if (dbg && blockIdx.x == 0 && threadIdx.x == 0)          // diagnostics: histogram of evaluator batch sizes (16 per bucket)
@@ -73,9 +75,8 @@ cudaError_t launch_trunk_x3(const NetWeights& w, const __nv_bfloat16* planes, fl
                             int max_rows, float* skip, int n_sm, cudaStream_t s, long long* dbg) {
     int pairs = n_sm / 2;
     if (max_rows < pairs) pairs = max_rows < 1 ? 1 : max_rows;
-    tc2::trunk_x3_kernel<<<2 * pairs, tc2::Cfg<2, true, true>::THREADS, tc2::X3_SMEM, s>>>(
-        w.res_w_x3p, w.conv_in_w_x3p, w.bias_blk_x3p, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, dbg);
-    return cudaGetLastError();
+    return launch_pdl(tc2::trunk_x3_kernel, dim3(2 * pairs), dim3(tc2::Cfg<2, true, true>::THREADS), tc2::X3_SMEM, s, w.res_w_x3p,
+                      w.conv_in_w_x3p, w.bias_blk_x3p, planes, w.head_w, headfeat, reinterpret_cast<uint4*>(skip), count, dbg);
 }
 
 }  // namespace uttt
